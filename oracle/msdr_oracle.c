@@ -1,0 +1,357 @@
+/* TEST INFRASTRUCTURE — CPU oracle for the Minimal-SDR receive DSP chain.
+ *
+ * A plain-C RESTATEMENT (written from the algorithm, not copied) of the reference's hot path:
+ *   fs/4 mix -> Q15 FIR pair -> SSB / AM demodulation -> fixed-point biquad cascade.
+ * Each function cites the reference file:line it follows.  Pinned against the reference itself:
+ * oracle/_ref/libmsdr_ref.so compiles the reference's own arm_fir_fast_q15.c / arm_fir_init_q15.c /
+ * arm_copy_q15.c / arm_sqrt_q31.c / filter_biquad.cpp (see oracle/Makefile); tests/test_oracle_vs_ref.py
+ * checks this file against it bit-for-bit, and tests/golden/ holds vectors generated from it
+ * (tests/golden/make_golden.py).  The reference repository ships no tests or golden vectors of its own.
+ * Exception — orc_freq_conv: the reference's freq_conv.cpp calls arm_mult_q15/arm_add_q15/arm_sub_q15,
+ * which are NOT vendored in the reference (CMSIS-DSP V1.5.1, prebuilt on Teensy) => parity unpinned
+ * for that one function; it restates the documented CMSIS semantics.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this
+ * library.  The product (minimal-sdr_b200/) never links or calls it and has no CPU fallback.
+ *
+ * Build: gcc -O2 -fwrapv -fno-strict-aliasing -fopenmp -shared -fPIC  (oracle/Makefile).
+ * All int32 arithmetic below that may overflow is done in uint32_t so it wraps like the Cortex-M4.
+ */
+#include <stdint.h>
+#include <stddef.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define ORC_BLOCK 128 /* AUDIO_BLOCK_SAMPLES (Teensy core; implied by Minimal-SDR.ino:113-114,525-526) */
+
+/* stations.h:4 */
+enum { ORC_SYNCAM = 0, ORC_AM = 1, ORC_LSB = 2, ORC_USB = 3, ORC_CW = 4 };
+
+static inline int32_t orc_ssat16(int32_t v) { return v > 32767 ? 32767 : (v < -32768 ? -32768 : v); }
+
+/* ------------------------------------------------------------------------------------------------
+ * A1  fs/4 mix.  Minimal-SDR.ino:546-558:  I = {x,0,-x,0}, Q = {0,x,0,-x} by n mod 4; the negation
+ * is computed in int and narrowed back to int16, so -(-32768) stays -32768.
+ */
+static inline int16_t orc_neg16(int16_t x) { return (int16_t)(uint16_t)(0u - (uint32_t)(int32_t)x); }
+
+void orc_mix_fs4(const int16_t *x, int16_t *I, int16_t *Q, uint32_t n)
+{
+  for (uint32_t i = 0; i < n; i++) {
+    switch (i & 3u) {
+    case 0: I[i] = x[i];            Q[i] = 0;                break;
+    case 1: I[i] = 0;               Q[i] = x[i];             break;
+    case 2: I[i] = orc_neg16(x[i]); Q[i] = 0;                break;
+    default: I[i] = 0;              Q[i] = orc_neg16(x[i]);  break;
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * A2/A3  Q15 FIR.  arm_fir_init_q15.c:78-138 (even numTaps >= 4 else ARGUMENT_ERROR, state zeroed,
+ * coefficient pointer kept) and arm_fir_fast_q15.c:60-329.  With s = hist[T-1] || block:
+ *   acc  = sum_{k<T} c[k]*s[n+k]   in a 32-bit register that WRAPS (SMLAD/SMLADX, :132-183)
+ *   y[n] = ssat16(acc >> 15)       (:234-238), then hist <- last T-1 of s (:296-327).
+ * The 4-way unrolled loop, the numTaps%4==2 tail (:195-227) and the blockSize%4 tail (:260-294)
+ * all compute this same sum; mod-2^32 addition is order independent, so direct form is exact.
+ */
+typedef struct {
+  uint16_t numTaps;
+  int16_t *coeffs; /* owned copy; orc_fir_set_coefficients models the reference's in-place rewrite */
+  int16_t *hist;   /* numTaps-1 carried samples */
+} orc_fir;
+
+orc_fir *orc_fir_new(uint16_t numTaps, const int16_t *coeffs, uint32_t blockSize, int *status)
+{
+  (void)blockSize;
+  orc_fir *f = (orc_fir *)calloc(1, sizeof(orc_fir));
+  f->numTaps = numTaps;
+  f->coeffs = (int16_t *)calloc((size_t)numTaps + 1, sizeof(int16_t));
+  f->hist = (int16_t *)calloc((size_t)numTaps + 1, sizeof(int16_t));
+  memcpy(f->coeffs, coeffs, (size_t)numTaps * sizeof(int16_t));
+  /* arm_fir_init_q15.c:93-96: "numTaps & 1" -> ARM_MATH_ARGUMENT_ERROR (-1).  (The header comment asks
+   * for >= 4 taps, the code only rejects odd counts.) */
+  if (status) *status = (numTaps & 1u) ? -1 : 0;
+  return f;
+}
+void orc_fir_set_coefficients(orc_fir *f, const int16_t *coeffs) { memcpy(f->coeffs, coeffs, (size_t)f->numTaps * sizeof(int16_t)); }
+void orc_fir_free(orc_fir *f) { if (f) { free(f->coeffs); free(f->hist); free(f); } }
+const int16_t *orc_fir_state(orc_fir *f) { return f->hist; }
+
+void orc_fir_run(orc_fir *f, const int16_t *src, int16_t *dst, uint32_t n)
+{
+  enum { CHUNK = 1024 };
+  const uint32_t T = f->numTaps, H = T - 1u;
+  int16_t stackbuf[CHUNK + 1024];
+  int16_t *s = (H + CHUNK <= sizeof(stackbuf) / sizeof(stackbuf[0])) ? stackbuf : (int16_t *)malloc(((size_t)H + CHUNK) * sizeof(int16_t));
+  for (uint32_t done = 0; done < n; done += CHUNK) {
+    const uint32_t m = (n - done < CHUNK) ? n - done : CHUNK;
+    memcpy(s, f->hist, (size_t)H * sizeof(int16_t));
+    memcpy(s + H, src + done, (size_t)m * sizeof(int16_t));
+    for (uint32_t i = 0; i < m; i++) {
+      uint32_t acc = 0;
+      for (uint32_t k = 0; k < T; k++) acc += (uint32_t)((int32_t)f->coeffs[k] * (int32_t)s[i + k]);
+      dst[done + i] = (int16_t)orc_ssat16((int32_t)acc >> 15);
+    }
+    memcpy(f->hist, s + m, (size_t)H * sizeof(int16_t));
+  }
+  if (s != stackbuf) free(s);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * A5c  arm_sqrt_q31.c:50-138.  CLZ normalisation, float initial guess via 0x5f3759df, three Newton
+ * steps in Q31 with 64-bit products, rescale.  in <= 0 -> 0 and ARM_MATH_ARGUMENT_ERROR.
+ */
+int orc_sqrt_q31(int32_t in, int32_t *pOut)
+{
+  if (in <= 0) { *pOut = 0; return -1; }
+  int32_t signBits = (int32_t)__builtin_clz((uint32_t)in) - 1;
+  int32_t sh = (signBits % 2 == 0) ? signBits : signBits - 1;
+  int32_t number = (int32_t)((uint32_t)in << sh);
+  int32_t half = number >> 1;
+  int32_t temp1 = number;
+  union { int32_t i; float f; } cv;
+  cv.f = (float)number * 4.6566128731e-010f;
+  cv.i = 0x5f3759df - (cv.i >> 1);
+  int32_t var1 = (int32_t)(cv.f * 1073741824.0f);
+  for (int it = 0; it < 3; it++) {
+    int32_t sq = (int32_t)(((int64_t)var1 * var1) >> 31);
+    int32_t t = (int32_t)(((int64_t)sq * (int64_t)half) >> 31);
+    int32_t d = (int32_t)(0x30000000u - (uint32_t)t);
+    var1 = (int32_t)((uint32_t)(int32_t)(((int64_t)var1 * d) >> 31) << 2);
+  }
+  var1 = (int32_t)((uint32_t)(int32_t)(((int64_t)temp1 * var1) >> 31) << 1);
+  var1 = var1 >> (sh / 2);
+  *pOut = var1;
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * A5  demodulation switch, Minimal-SDR.ino:589-628.
+ *   kind 0 LSB  (:591-596)  out = (int16)(I - Q)           plain int add, narrowing store wraps
+ *   kind 1 USB  (:598-604)  out = (int16)(I + Q)
+ *   kind 2 AM/CW f32 (:606-616, arm_math.h:5733-5760)  s = I*I+Q*Q (int32, wraps only for I=Q=-32768);
+ *          r = s >= 0 ? sqrtf((float)s) : 0;  out = (int16)(int32)r   (truncate, then keep low 16 bits)
+ *   kind 3 AM/CW/SYNCAM q31 (:617-627)  out = (int16)(arm_sqrt_q31(s) >> 16)
+ */
+void orc_demod(int kind, const int16_t *I, const int16_t *Q, int16_t *out, uint32_t n)
+{
+  for (uint32_t i = 0; i < n; i++) {
+    const int32_t a = I[i], b = Q[i];
+    switch (kind) {
+    case 0: out[i] = (int16_t)(uint16_t)(uint32_t)(a - b); break;
+    case 1: out[i] = (int16_t)(uint16_t)(uint32_t)(a + b); break;
+    case 2: {
+      int32_t s = (int32_t)((uint32_t)(a * a) + (uint32_t)(b * b));
+      float fs = (float)s;
+      float r = (fs >= 0.0f) ? sqrtf(fs) : 0.0f;
+      out[i] = (int16_t)(uint16_t)(uint32_t)(int32_t)r;
+      break;
+    }
+    case 3: {
+      int32_t s = (int32_t)((uint32_t)(a * a) + (uint32_t)(b * b));
+      int32_t r;
+      orc_sqrt_q31(s, &r);
+      out[i] = (int16_t)(uint16_t)(uint32_t)(r >> 16);
+      break;
+    }
+    default: break;
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * A7/A8  AudioFilterBiquad.  State `definition[32]` (filter_biquad.h:152): 4 stages x
+ *   {b0, b1, b2, -a1, -a2, bprev = x[n-1]:x[n-2], aprev = y[n-1]:y[n-2], residual | flag(bit31)}.
+ * update() (filter_biquad.cpp:33-82), per stage and sample:
+ *   sum = residual + sum_i trunc32((int64)coef_i * v_i >> 16)     five SMLAWB/SMLAWT, adds wrap
+ *   y   = ssat16(sum >> 14)                                       (ssat #16, asr #14; dspinst.h:33-51)
+ *   residual = sum & 0x3FFF
+ * Stages run stage-major over the 128-sample block, the next stage runs iff bit31 of word 7 is set.
+ * setCoefficients (filter_biquad.cpp:84-100): stage >= 4 ignored; sets the flag on the PREVIOUS stage;
+ * stores b0,b1,b2,-a1,-a2; keeps x/y history; clears the residual but keeps this stage's flag.
+ */
+typedef struct { int32_t definition[32]; } orc_biquad;
+
+orc_biquad *orc_biquad_new(void) { return (orc_biquad *)calloc(1, sizeof(orc_biquad)); } /* filter_biquad.h:36-39 */
+void orc_biquad_free(orc_biquad *b) { free(b); }
+void orc_biquad_get_definition(orc_biquad *b, int32_t *out32) { memcpy(out32, b->definition, sizeof(b->definition)); }
+void orc_biquad_set_definition(orc_biquad *b, const int32_t *in32) { memcpy(b->definition, in32, sizeof(b->definition)); }
+
+void orc_biquad_set_coefficients(orc_biquad *b, uint32_t stage, const int32_t *coef)
+{
+  if (stage >= 4) return;
+  int32_t *dest = b->definition + (stage << 3);
+  if (stage > 0) dest[-1] = (int32_t)((uint32_t)dest[-1] | 0x80000000u);
+  dest[0] = coef[0];
+  dest[1] = coef[1];
+  dest[2] = coef[2];
+  dest[3] = (int32_t)(0u - (uint32_t)coef[3]);
+  dest[4] = (int32_t)(0u - (uint32_t)coef[4]);
+  dest[7] = (int32_t)((uint32_t)dest[7] & 0x80000000u);
+}
+
+static inline uint32_t orc_smulw(int32_t c, int32_t v16) { return (uint32_t)(int32_t)(((int64_t)c * (int64_t)v16) >> 16); }
+
+void orc_biquad_update(orc_biquad *b, int16_t *block, uint32_t n /* even; 128 in the reference */)
+{
+  int32_t *st = b->definition;
+  uint32_t flag;
+  do {
+    const int32_t b0 = st[0], b1 = st[1], b2 = st[2], a1 = st[3], a2 = st[4];
+    int32_t x1 = (int16_t)((uint32_t)st[5] >> 16), x2 = (int16_t)((uint32_t)st[5] & 0xFFFF);
+    int32_t y1 = (int16_t)((uint32_t)st[6] >> 16), y2 = (int16_t)((uint32_t)st[6] & 0xFFFF);
+    uint32_t sum = (uint32_t)st[7] & 0x3FFFu;
+    for (uint32_t i = 0; i < n; i++) {
+      const int32_t x0 = block[i];
+      sum += orc_smulw(b0, x0) + orc_smulw(b1, x1) + orc_smulw(b2, x2) + orc_smulw(a1, y1) + orc_smulw(a2, y2);
+      const int32_t y0 = orc_ssat16((int32_t)sum >> 14);
+      sum &= 0x3FFFu;
+      x2 = x1; x1 = x0; y2 = y1; y1 = y0;
+      block[i] = (int16_t)y0;
+    }
+    flag = (uint32_t)st[7] & 0x80000000u;
+    st[7] = (int32_t)(sum | flag);
+    st[6] = (int32_t)(((uint32_t)y1 << 16) | ((uint32_t)y2 & 0xFFFFu));
+    st[5] = (int32_t)(((uint32_t)x1 << 16) | ((uint32_t)x2 & 0xFFFFu));
+    st += 8;
+  } while (flag);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * A6  AudioEffectFreqConv::update, freq_conv.cpp:30-116 (dead code in the sketch).  PARITY UNPINNED:
+ * arm_mult_q15 = ssat16((a*b)>>15), arm_add_q15 / arm_sub_q15 saturating (CMSIS-DSP V1.5.1 docs).
+ * pass == 0 forwards the inputs unchanged (freq_conv.cpp:49-56; note the inverted naming).
+ */
+static inline int16_t orc_mult_q15(int16_t a, int16_t b) { return (int16_t)orc_ssat16(((int32_t)a * b) >> 15); }
+
+void orc_freq_conv(int dir, int pass, int16_t *I, int16_t *Q, const int16_t *oscI, const int16_t *oscQ, uint32_t n)
+{
+  if (!pass) return;
+  for (uint32_t i = 0; i < n; i++) {
+    const int16_t vi = I[i], vq = Q[i];
+    if (!dir) {
+      const int32_t A = orc_mult_q15(vi, oscQ[i]), B = orc_mult_q15(vq, oscI[i]);
+      const int32_t C = orc_mult_q15(vq, oscQ[i]), D = orc_mult_q15(vi, oscI[i]);
+      I[i] = (int16_t)orc_ssat16(A + B);
+      Q[i] = (int16_t)orc_ssat16(C - D);
+    } else {
+      const int32_t A = orc_mult_q15(vq, oscQ[i]), B = orc_mult_q15(vi, oscI[i]);
+      const int32_t C = orc_mult_q15(vi, oscQ[i]), D = orc_mult_q15(vq, oscI[i]);
+      Q[i] = (int16_t)orc_ssat16(A + B);
+      I[i] = (int16_t)orc_ssat16(C - D);
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Whole chain, batched over independent channels: demodulation() (Minimal-SDR.ino:518-775, CS-1) followed
+ * by biquad1_dac.update(), biquad2_dac.update() of the IRQ graph (CS-2; .ino:71-72,77,79-80).
+ */
+typedef struct {
+  int mode;
+  orc_fir *fir_i, *fir_q;
+  orc_biquad bq[2];
+} orc_channel;
+
+typedef struct {
+  uint32_t n_channels;
+  int am_q31;
+  orc_channel *ch;
+} orc_chain;
+
+orc_chain *orc_chain_new(uint32_t n_channels, int am_q31)
+{
+  orc_chain *c = (orc_chain *)calloc(1, sizeof(orc_chain));
+  c->n_channels = n_channels;
+  c->am_q31 = am_q31;
+  c->ch = (orc_channel *)calloc(n_channels, sizeof(orc_channel));
+  for (uint32_t i = 0; i < n_channels; i++) c->ch[i].mode = ORC_AM; /* .ino:98 */
+  return c;
+}
+void orc_chain_free(orc_chain *c)
+{
+  if (!c) return;
+  for (uint32_t i = 0; i < c->n_channels; i++) { orc_fir_free(c->ch[i].fir_i); orc_fir_free(c->ch[i].fir_q); }
+  free(c->ch); free(c);
+}
+int orc_chain_set_mode(orc_chain *c, uint32_t ch0, uint32_t nch, int mode)
+{
+  if (ch0 + nch > c->n_channels || mode < 0 || mode > 4) return -1;
+  for (uint32_t i = ch0; i < ch0 + nch; i++) c->ch[i].mode = mode;
+  return 0;
+}
+int orc_chain_fir_init(orc_chain *c, uint32_t ch0, uint32_t nch, uint16_t numTaps, const int16_t *cI, const int16_t *cQ)
+{
+  if (ch0 + nch > c->n_channels) return -1;
+  int st = 0, s1, s2;
+  for (uint32_t i = ch0; i < ch0 + nch; i++) {
+    orc_fir_free(c->ch[i].fir_i); orc_fir_free(c->ch[i].fir_q);
+    c->ch[i].fir_i = orc_fir_new(numTaps, cI, ORC_BLOCK, &s1);
+    c->ch[i].fir_q = orc_fir_new(numTaps, cQ, ORC_BLOCK, &s2);
+    if (s1) st = s1;
+    if (s2) st = s2;
+  }
+  return st;
+}
+int orc_chain_fir_set_coefficients(orc_chain *c, uint32_t ch0, uint32_t nch, const int16_t *cI, const int16_t *cQ)
+{
+  if (ch0 + nch > c->n_channels) return -1;
+  for (uint32_t i = ch0; i < ch0 + nch; i++) {
+    if (!c->ch[i].fir_i) return -1;
+    orc_fir_set_coefficients(c->ch[i].fir_i, cI);
+    orc_fir_set_coefficients(c->ch[i].fir_q, cQ);
+  }
+  return 0;
+}
+int orc_chain_biquad_set_coefficients(orc_chain *c, int obj, uint32_t ch0, uint32_t nch, uint32_t stage, const int32_t *coef)
+{
+  if (ch0 + nch > c->n_channels || obj < 0 || obj > 1) return -1;
+  for (uint32_t i = ch0; i < ch0 + nch; i++) orc_biquad_set_coefficients(&c->ch[i].bq[obj], stage, coef);
+  return 0;
+}
+/* state access for checkpoint/resume tests: raw FIR history is reconstructed from the I/Q delay lines
+ * (even positions live in the I line, odd ones in the Q line; samples at n%4 in {2,3} were negated). */
+void orc_chain_get_biquad_definition(orc_chain *c, uint32_t ch, int obj, int32_t *out32) { memcpy(out32, c->ch[ch].bq[obj].definition, 128); }
+
+static int orc_demod_kind(const orc_chain *c, int mode)
+{
+  switch (mode) {
+  case ORC_LSB: return 0;
+  case ORC_USB: return 1;
+  case ORC_CW:
+  case ORC_AM:  return c->am_q31 ? 3 : 2;
+  default:      return 3; /* SYNCAM shares the q31 envelope on Teensy 3.2 (.ino:618-620); f32 PLL is a "next" row */
+  }
+}
+
+int orc_chain_run(orc_chain *c, const int16_t *in, int16_t *out, uint32_t n_blocks, size_t stride, int n_threads)
+{
+  int used = 1;
+#ifdef _OPENMP
+  if (n_threads > 0) omp_set_num_threads(n_threads);
+  used = omp_get_max_threads();
+#pragma omp parallel for schedule(static)
+#endif
+  for (long i = 0; i < (long)c->n_channels; i++) {
+    orc_channel *k = &c->ch[i];
+    if (!k->fir_i || !k->fir_q) continue;
+    int16_t I[ORC_BLOCK], Q[ORC_BLOCK], If[ORC_BLOCK], Qf[ORC_BLOCK];
+    const int kind = orc_demod_kind(c, k->mode);
+    for (uint32_t b = 0; b < n_blocks; b++) {
+      const int16_t *p_adc = in + (size_t)i * stride + (size_t)b * ORC_BLOCK;
+      int16_t *p_dac = out + (size_t)i * stride + (size_t)b * ORC_BLOCK;
+      orc_mix_fs4(p_adc, I, Q, ORC_BLOCK);
+      orc_fir_run(k->fir_i, I, If, ORC_BLOCK);
+      orc_fir_run(k->fir_q, Q, Qf, ORC_BLOCK);
+      orc_demod(kind, If, Qf, p_dac, ORC_BLOCK);
+      orc_biquad_update(&k->bq[0], p_dac, ORC_BLOCK);
+      orc_biquad_update(&k->bq[1], p_dac, ORC_BLOCK);
+    }
+  }
+  return used;
+}
