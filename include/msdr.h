@@ -1,0 +1,163 @@
+/* msdr.h — C ABI of the B200-native Minimal-SDR receive DSP chain.
+ *
+ * Drop-in boundary for ONE path of FrankBoesing/Minimal-SDR: what `demodulation()`
+ * (Minimal-SDR.ino:518-775) does per 128-sample block — fs/4 mix, arm_fir_fast_q15 on I and Q,
+ * SSB / AM demodulation — followed by the two AudioFilterBiquad objects of the audio graph
+ * (Minimal-SDR.ino:71-72, src/Audio/filter_biquad.cpp:33-82), batched over independent channels and
+ * executed by hand-written CUDA kernels for sm_100a.  There is no CPU fallback: every entry point that
+ * computes needs a CUDA device and fails with MSDR_ERR_CUDA otherwise.
+ *
+ * Conventions
+ *   - plain C types only; all buffers are caller-owned; a chain owns its device state and its copies of
+ *     the coefficients (the reference's FIR borrows the table pointer, arm_fir_init_q15.c:103 — here
+ *     msdr_fir_set_coefficients() models an in-place rewrite of that table, Minimal-SDR.ino:222).
+ *   - sample buffers are int16 [n_channels][stride] row-major, `n_blocks*128` samples used per row.
+ *   - return value: 0 = success; negative = error.  -1..-6 carry the values of CMSIS `arm_status`
+ *     (arm_math.h:404-413) so `msdr_fir_init_q15` reports odd tap counts exactly like
+ *     `arm_fir_init_q15` (arm_fir_init_q15.c:93-96).
+ *   - a chain is not thread-safe; setters are stream-ordered and take effect at the next update, i.e. at
+ *     a block boundary, like the reference's __disable_irq()/AudioNoInterrupts() sections
+ *     (filter_biquad.cpp:88-99, Minimal-SDR.ino:336-367).
+ */
+#ifndef MSDR_H
+#define MSDR_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSDR_BLOCK_SAMPLES 128   /* AUDIO_BLOCK_SAMPLES (Teensy core; Minimal-SDR.ino:113-114) */
+#define MSDR_MAX_TAPS 256        /* BASELINE config 4: 255 taps + zero pad (arm_fir_init_q15.c:55-64) */
+#define MSDR_MAX_FIR_SETS 32     /* distinct (numTaps, cI, cQ) tables alive in one chain */
+#define MSDR_BIQUAD_OBJECTS 2    /* biquad1_dac, biquad2_dac (Minimal-SDR.ino:71-72) */
+#define MSDR_BIQUAD_STAGES 4     /* filter_biquad.h:152: int32_t definition[32] = 4 stages x 8 words */
+
+typedef enum {
+  MSDR_OK = 0,
+  MSDR_ERR_ARGUMENT = -1,       /* == ARM_MATH_ARGUMENT_ERROR */
+  MSDR_ERR_LENGTH = -2,         /* == ARM_MATH_LENGTH_ERROR */
+  MSDR_ERR_CUDA = -100,         /* CUDA runtime/driver failure or no device; see msdr_last_error() */
+  MSDR_ERR_UNSUPPORTED = -101,
+  MSDR_ERR_NOMEM = -102,
+  MSDR_ERR_NOT_INITIALISED = -103 /* update() on a channel whose FIR was never initialised */
+} msdr_status;
+
+/* stations.h:4  enum { SYNCAM, AM, LSB, USB, CW } — same numeric values */
+typedef enum { MSDR_MODE_SYNCAM = 0, MSDR_MODE_AM = 1, MSDR_MODE_LSB = 2, MSDR_MODE_USB = 3, MSDR_MODE_CW = 4 } msdr_mode;
+
+/* chain flags */
+#define MSDR_FLAG_AM_Q31 1u /* Teensy 3.2 arithmetic: AM/CW/SYNCAM envelope via arm_sqrt_q31 (Minimal-SDR.ino:617-627)
+                               instead of the Teensy 3.5/3.6 arm_sqrt_f32 path (:606-616) */
+
+typedef struct msdr_chain msdr_chain;
+
+/* Per-channel state, for checkpoint / resume / migration between GPUs. */
+typedef struct {
+  int32_t mode;                                 /* msdr_mode */
+  uint32_t num_taps;                            /* 0 = FIR not initialised */
+  int32_t fir_set;                              /* coefficient-set id inside this chain, -1 = none */
+  int16_t fir_history[MSDR_MAX_TAPS];           /* last num_taps-1 RAW ADC samples, oldest first, in [0, num_taps-1);
+                                                   the reference's two pState delay lines (arm_fir_fast_q15.c:296-327) are
+                                                   this sequence after the fs/4 mix */
+  int32_t biquad_definition[MSDR_BIQUAD_OBJECTS][32]; /* filter_biquad.h:152 layout, verbatim */
+} msdr_channel_state;
+
+/* ---- lifetime -------------------------------------------------------------------------------- */
+
+/* Creates a chain of n_channels independent receive channels on CUDA device `device`.
+ * max_taps (even, 4..MSDR_MAX_TAPS; 0 = 102, the reference's MAX_num_taps, Minimal-SDR.ino:110) bounds the FIR
+ * length and sizes the per-channel history.  All channels start in mode AM (Minimal-SDR.ino:98) with
+ * both biquad objects zeroed — "by default, the filter will not pass anything" (filter_biquad.h:36-39) —
+ * and no FIR bound (the sketch always calls init_FIR() in setup(), Minimal-SDR.ino:404). */
+int msdr_chain_create(msdr_chain **out, int device, uint32_t n_channels, uint32_t max_taps, uint32_t flags);
+void msdr_chain_destroy(msdr_chain *chain);
+/* Runs the chain's work on a caller-provided cudaStream_t (e.g. torch's current stream); NULL = own stream. */
+int msdr_chain_set_stream(msdr_chain *chain, void *cuda_stream);
+int msdr_chain_synchronize(msdr_chain *chain);
+const char *msdr_last_error(const msdr_chain *chain); /* chain may be NULL: error of the last failed create */
+uint32_t msdr_chain_channels(const msdr_chain *chain);
+
+/* ---- configuration (the reference's globals and setters, per channel range [ch0, ch0+nch)) ---- */
+
+/* `mode = ...` (Minimal-SDR.ino:98; UI.cpp mode menu).  Only selects the demodulation branch
+ * (Minimal-SDR.ino:589); like the reference, re-binding FIR tables is a separate call (init_FIR via tune()). */
+int msdr_chain_set_mode(msdr_chain *chain, uint32_t ch0, uint32_t nch, int mode);
+
+/* arm_fir_init_q15 x2 as in init_FIR() (Minimal-SDR.ino:901-930; arm_math.h:1106-1128): zeroes the delay lines of
+ * the channels and binds taps cI (I branch) and cQ (Q branch), `numTaps` each, in the reference's
+ * "time reversed" order (arm_fir_init_q15.c:50-54).  Odd numTaps -> MSDR_ERR_ARGUMENT and nothing changes. */
+int msdr_fir_init_q15(msdr_chain *chain, uint32_t ch0, uint32_t nch, uint16_t numTaps, const int16_t *cI, const int16_t *cQ);
+
+/* In-place rewrite of the bound tables (calc_demod_filter(), Minimal-SDR.ino:221-223 / UI.cpp:337-345): same tap
+ * count, delay lines kept.  All channels in the range must currently share one table. */
+int msdr_fir_set_coefficients(msdr_chain *chain, uint32_t ch0, uint32_t nch, const int16_t *cI, const int16_t *cQ);
+
+/* AudioFilterBiquad::setCoefficients(stage, const int *) (filter_biquad.cpp:84-100) on object `object`
+ * (0 = biquad1_dac, 1 = biquad2_dac): coef = {b0,b1,b2,a1,a2} in Q2.30; a1,a2 are stored negated; the previous
+ * stage gets its "another stage follows" flag; x/y history kept; residual cleared; stage >= 4 silently ignored. */
+int msdr_biquad_set_coefficients(msdr_chain *chain, int object, uint32_t ch0, uint32_t nch, uint32_t stage, const int32_t *coef);
+
+/* ---- the hot path ------------------------------------------------------------------------------ */
+
+/* One `update_all()` worth of work for every channel, n_blocks AudioStream blocks deep:
+ * out[c][n] = biquad2(biquad1(demod(FIR_I(mixI(in[c])), FIR_Q(mixQ(in[c]))))), state carried across calls.
+ * HOST buffers: copies in, runs, copies out, returns when `out` is complete.  Pinned buffers
+ * (msdr_host_alloc) make the copies overlap the kernels. */
+int msdr_chain_update(msdr_chain *chain, const int16_t *in, int16_t *out, uint32_t n_blocks, size_t stride);
+
+/* Same on DEVICE buffers, asynchronous on the chain's stream.  in/out must be 16-byte aligned, stride a multiple
+ * of 8 samples; in and out may not overlap. */
+int msdr_chain_update_device(msdr_chain *chain, const int16_t *d_in, int16_t *d_out, uint32_t n_blocks, size_t stride);
+
+/* Device time of the last update in milliseconds (CUDA events), the analogue of the reference's
+ * micros()-around-demodulation() load figure (Minimal-SDR.ino:533,774; :415-432). Synchronises. */
+int msdr_chain_last_update_ms(msdr_chain *chain, float *ms);
+/* Number of kernels launched by this chain since creation (bench.py reports it as gpu_launches). */
+uint64_t msdr_chain_launch_count(const msdr_chain *chain);
+
+int msdr_chain_get_state(msdr_chain *chain, uint32_t ch, msdr_channel_state *out);
+int msdr_chain_set_state(msdr_chain *chain, uint32_t ch, const msdr_channel_state *in);
+
+/* Kernel selection for studies (bench.py / tests): 0 = default. See DESIGN.md "Kernels". */
+int msdr_chain_set_option(msdr_chain *chain, const char *key, int value);
+
+/* pinned host memory for update() */
+void *msdr_host_alloc(size_t bytes);
+void msdr_host_free(void *p);
+
+/* ---- stage-level batched operators (one reference primitive each; HOST buffers) ------------------
+ * Used by the AudioStream façade (include/msdr/Audio.h) and by the per-stage parity tests. `rows`
+ * independent streams of `n` samples each, row-major with the given stride. */
+
+/* fs/4 mix, Minimal-SDR.ino:546-558.  n % 4 == 0. */
+int msdr_op_mix_fs4(int device, const int16_t *in, int16_t *outI, int16_t *outQ, uint32_t rows, uint32_t n, size_t stride);
+
+/* arm_fir_fast_q15 (arm_fir_fast_q15.c:60-329) over `rows` streams sharing one tap table.  history: int16
+ * [rows][numTaps-1] in/out (NULL = zero history, not written back) — the first numTaps-1 entries of pState. */
+int msdr_op_fir_fast_q15(int device, uint16_t numTaps, const int16_t *coeffs, int16_t *history,
+                         const int16_t *in, int16_t *out, uint32_t rows, uint32_t n, size_t stride);
+
+/* demodulation switch, Minimal-SDR.ino:589-628.  kind: 0 LSB, 1 USB, 2 AM/CW f32, 3 AM/CW/SYNCAM q31. */
+int msdr_op_demod(int device, int kind, const int16_t *I, const int16_t *Q, int16_t *out, uint32_t rows, uint32_t n, size_t stride);
+
+/* AudioFilterBiquad::update (filter_biquad.cpp:33-82) over `rows` streams, in place, n % 2 == 0.
+ * definition: int32 [rows][32] in/out, filter_biquad.h:152 layout. */
+int msdr_op_biquad(int device, int32_t *definition, int16_t *data, uint32_t rows, uint32_t n, size_t stride);
+
+/* AudioEffectFreqConv::update (freq_conv.cpp:30-116), in place on I and Q; oscI/oscQ: int16[n] tables
+ * shared by all rows (the sketch's Osc_I_buffer_i / Osc_Q_buffer_i, freq_conv.h:33-34). */
+int msdr_op_freq_conv(int device, int dir, int pass, int16_t *I, int16_t *Q, const int16_t *oscI, const int16_t *oscQ,
+                      uint32_t rows, uint32_t n, size_t stride);
+
+/* arm_sqrt_q31 (arm_sqrt_q31.c:50-138) element-wise; status[i] = 0 or -1 like arm_status (may be NULL). */
+int msdr_op_sqrt_q31(int device, const int32_t *in, int32_t *out, int32_t *status, uint32_t n);
+
+const char *msdr_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSDR_H */

@@ -1,0 +1,563 @@
+// msdr_capi.cu — the C ABI declared in include/msdr.h: chain object, configuration, updates, stage operators.
+// Host-side only plumbing; every computation is a CUDA kernel from msdr_chain_kernel.cu / msdr_stage_kernels.cu.
+#include "../../include/msdr.h"
+#include "msdr_internal.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace msdr;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct FirSet {
+  uint32_t T = 0;
+  std::vector<int16_t> cI, cQ;
+  uint32_t users = 0;
+};
+
+// Expand one (cI, cQ) table into the four polyphase sub-filters the fused kernel consumes.
+// Output layout: [kp4 chunks][4 filters A,B,C,D][4 taps] int32, KP = 4*kp4 = roundup4(T/2 + 1).
+// With k' = d - (KP - T/2):  A[d] = cI[2k'], B[d] = cI[2k'+1], C[d] = cQ[2k'+1], D[d] = cQ[2(k'+1)], zero outside.
+// Derivation in DESIGN.md ("Polyphase form of the fs/4 mix + FIR").
+void expand_set(const FirSet &s, std::vector<int32_t> &out, uint32_t stride_words)
+{
+  out.assign(stride_words, 0);
+  const int T = (int)s.T, half = T / 2, KP = (int)kp_of_taps(s.T);
+  for (int d = 0; d < KP; ++d) {
+    const int kq = d - (KP - half);
+    int a = 0, b = 0, c = 0, dd = 0;
+    if (kq >= 0 && kq < half) { a = s.cI[2 * kq]; b = s.cI[2 * kq + 1]; c = s.cQ[2 * kq + 1]; }
+    if (kq + 1 >= 0 && kq + 1 < half) dd = s.cQ[2 * (kq + 1)];
+    const int chunk = d / 4, t = d % 4;
+    out[(size_t)chunk * 16 + 0 + t] = a;
+    out[(size_t)chunk * 16 + 4 + t] = b;
+    out[(size_t)chunk * 16 + 8 + t] = c;
+    out[(size_t)chunk * 16 + 12 + t] = dd;
+  }
+}
+
+} // namespace
+
+struct msdr_chain {
+  int device = 0;
+  uint32_t C = 0, Cpad = 0, max_taps = 0, KPmax = 0, H = 0, flags = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr, copy_in = nullptr, copy_out = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::vector<cudaEvent_t> pipe_ev;
+  bool timed = false;
+
+  std::vector<uint8_t> h_mode, h_set; // h_set: 0xFF = FIR not initialised
+  uint32_t n_uninit = 0;
+  std::vector<FirSet> sets;
+  uint32_t set_stride_words = 0;
+
+  uint8_t *d_mode = nullptr, *d_set = nullptr;
+  int16_t *d_hist = nullptr;
+  int32_t *d_bq = nullptr;
+  int32_t *d_sets = nullptr;
+  uint32_t *d_set_kp4 = nullptr;
+  int *d_ctrl = nullptr;
+
+  // staging for host-buffer updates
+  int16_t *d_in = nullptr, *d_out = nullptr;
+  size_t stage_samples = 0; // per buffer
+  int16_t *pin_in = nullptr, *pin_out = nullptr;
+  size_t pin_samples = 0;
+
+  int variant = 0;
+  uint32_t host_chunk_channels = 0; // 0 = auto
+  uint64_t launches = 0;
+  std::string err;
+  ChainLaunchInfo last_info{};
+};
+
+namespace {
+
+int fail(msdr_chain *c, int code, const std::string &msg)
+{
+  if (c) c->err = msg; else g_create_error = msg;
+  return code;
+}
+int cuda_fail(msdr_chain *c, cudaError_t e, const char *what)
+{
+  return fail(c, MSDR_ERR_CUDA, std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")");
+}
+#define CK(call)                                             \
+  do {                                                       \
+    cudaError_t e__ = (call);                                \
+    if (e__ != cudaSuccess) return cuda_fail(chain, e__, #call); \
+  } while (0)
+
+bool range_ok(const msdr_chain *c, uint32_t ch0, uint32_t nch) { return (uint64_t)ch0 + nch <= c->C; }
+
+int upload_set(msdr_chain *chain, uint32_t id)
+{
+  std::vector<int32_t> ex;
+  expand_set(chain->sets[id], ex, chain->set_stride_words);
+  const uint32_t kp4 = kp_of_taps(chain->sets[id].T) / 4;
+  CK(cudaMemcpyAsync(chain->d_sets + (size_t)id * chain->set_stride_words, ex.data(), ex.size() * sizeof(int32_t), cudaMemcpyHostToDevice,
+                     chain->stream));
+  CK(cudaMemcpyAsync(chain->d_set_kp4 + id, &kp4, sizeof(kp4), cudaMemcpyHostToDevice, chain->stream));
+  CK(cudaStreamSynchronize(chain->stream)); // `ex` and `kp4` are stack/heap temporaries
+  return MSDR_OK;
+}
+
+// find or create a coefficient set; returns id or negative status
+int intern_set(msdr_chain *chain, uint32_t T, const int16_t *cI, const int16_t *cQ)
+{
+  for (size_t i = 0; i < chain->sets.size(); ++i) {
+    const FirSet &s = chain->sets[i];
+    if (s.T == T && s.users > 0 && !memcmp(s.cI.data(), cI, T * 2) && !memcmp(s.cQ.data(), cQ, T * 2)) return (int)i;
+  }
+  size_t slot = chain->sets.size();
+  for (size_t i = 0; i < chain->sets.size(); ++i)
+    if (chain->sets[i].users == 0) { slot = i; break; }
+  if (slot == chain->sets.size()) {
+    if (slot >= MSDR_MAX_FIR_SETS) return fail(chain, MSDR_ERR_NOMEM, "more than MSDR_MAX_FIR_SETS distinct FIR tables in one chain");
+    chain->sets.emplace_back();
+  }
+  FirSet &s = chain->sets[slot];
+  s.T = T;
+  s.cI.assign(cI, cI + T);
+  s.cQ.assign(cQ, cQ + T);
+  s.users = 0;
+  int st = upload_set(chain, (uint32_t)slot);
+  if (st != MSDR_OK) return st;
+  return (int)slot;
+}
+
+int assign_set(msdr_chain *chain, uint32_t ch0, uint32_t nch, uint32_t id)
+{
+  for (uint32_t c = ch0; c < ch0 + nch; ++c) {
+    const uint8_t old = chain->h_set[c];
+    if (old == 0xFF) chain->n_uninit--; else chain->sets[old].users--;
+    chain->h_set[c] = (uint8_t)id;
+  }
+  chain->sets[id].users += nch;
+  CK(cudaMemcpyAsync(chain->d_set + ch0, chain->h_set.data() + ch0, nch, cudaMemcpyHostToDevice, chain->stream));
+  CK(cudaStreamSynchronize(chain->stream));
+  return MSDR_OK;
+}
+
+int ensure_stage(msdr_chain *chain, size_t samples)
+{
+  if (chain->stage_samples >= samples) return MSDR_OK;
+  if (chain->d_in) cudaFree(chain->d_in);
+  if (chain->d_out) cudaFree(chain->d_out);
+  chain->d_in = chain->d_out = nullptr;
+  chain->stage_samples = 0;
+  CK(cudaMalloc(&chain->d_in, samples * sizeof(int16_t)));
+  CK(cudaMalloc(&chain->d_out, samples * sizeof(int16_t)));
+  chain->stage_samples = samples;
+  return MSDR_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+const char *msdr_version(void) { return "minimal-sdr_b200 0.1 (sm_100a)"; }
+
+int msdr_chain_create(msdr_chain **out, int device, uint32_t n_channels, uint32_t max_taps, uint32_t flags)
+{
+  if (!out) return fail(nullptr, MSDR_ERR_ARGUMENT, "out == NULL");
+  *out = nullptr;
+  if (max_taps == 0) max_taps = 102;
+  if (n_channels == 0 || (max_taps & 1u) || max_taps < 4 || max_taps > MSDR_MAX_TAPS)
+    return fail(nullptr, MSDR_ERR_ARGUMENT, "n_channels must be > 0 and max_taps even in [4, MSDR_MAX_TAPS]");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return fail(nullptr, MSDR_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(nullptr, MSDR_ERR_ARGUMENT, "bad device index");
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return cuda_fail(nullptr, e, "cudaGetDeviceProperties");
+  if (prop.major != 10) return fail(nullptr, MSDR_ERR_UNSUPPORTED, "kernels are built for sm_100a (B200) only");
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return cuda_fail(nullptr, e, "cudaSetDevice");
+
+  msdr_chain *chain = new msdr_chain();
+  chain->device = device;
+  chain->C = n_channels;
+  chain->Cpad = (n_channels + 31u) & ~31u;
+  chain->max_taps = max_taps;
+  chain->KPmax = kp_of_taps(max_taps);
+  chain->H = hist_of_kp(chain->KPmax);
+  chain->flags = flags;
+  chain->set_stride_words = chain->KPmax * 4; // kp4 chunks x 16 words
+  chain->h_mode.assign(n_channels, (uint8_t)MSDR_MODE_AM);
+  chain->h_set.assign(n_channels, 0xFF);
+  chain->n_uninit = n_channels;
+
+  auto bail = [&](cudaError_t ee, const char *what) {
+    int st = cuda_fail(nullptr, ee, what);
+    msdr_chain_destroy(chain);
+    return st;
+  };
+#define CKC(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return bail(e__, #call); } while (0)
+  CKC(cudaStreamCreateWithFlags(&chain->own_stream, cudaStreamNonBlocking));
+  CKC(cudaStreamCreateWithFlags(&chain->copy_in, cudaStreamNonBlocking));
+  CKC(cudaStreamCreateWithFlags(&chain->copy_out, cudaStreamNonBlocking));
+  chain->stream = chain->own_stream;
+  CKC(cudaEventCreate(&chain->ev0));
+  CKC(cudaEventCreate(&chain->ev1));
+  CKC(cudaMalloc(&chain->d_mode, n_channels));
+  CKC(cudaMalloc(&chain->d_set, n_channels));
+  CKC(cudaMalloc(&chain->d_hist, (size_t)n_channels * chain->H * sizeof(int16_t)));
+  CKC(cudaMalloc(&chain->d_bq, (size_t)kBqWords * chain->Cpad * sizeof(int32_t)));
+  CKC(cudaMalloc(&chain->d_sets, (size_t)MSDR_MAX_FIR_SETS * chain->set_stride_words * sizeof(int32_t)));
+  CKC(cudaMalloc(&chain->d_set_kp4, MSDR_MAX_FIR_SETS * sizeof(uint32_t)));
+  CKC(cudaMalloc(&chain->d_ctrl, (size_t)(1 + chain->Cpad / kGroup + 1) * sizeof(int)));
+  CKC(cudaMemsetAsync(chain->d_mode, MSDR_MODE_AM, n_channels, chain->stream));
+  CKC(cudaMemsetAsync(chain->d_set, 0, n_channels, chain->stream));
+  CKC(cudaMemsetAsync(chain->d_hist, 0, (size_t)n_channels * chain->H * sizeof(int16_t), chain->stream));
+  CKC(cudaMemsetAsync(chain->d_bq, 0, (size_t)kBqWords * chain->Cpad * sizeof(int32_t), chain->stream));
+  CKC(cudaMemsetAsync(chain->d_sets, 0, (size_t)MSDR_MAX_FIR_SETS * chain->set_stride_words * sizeof(int32_t), chain->stream));
+  CKC(cudaMemsetAsync(chain->d_set_kp4, 0, MSDR_MAX_FIR_SETS * sizeof(uint32_t), chain->stream));
+  CKC(cudaStreamSynchronize(chain->stream));
+#undef CKC
+  *out = chain;
+  return MSDR_OK;
+}
+
+void msdr_chain_destroy(msdr_chain *chain)
+{
+  if (!chain) return;
+  cudaSetDevice(chain->device);
+  if (chain->stream) cudaStreamSynchronize(chain->stream);
+  cudaFree(chain->d_mode); cudaFree(chain->d_set); cudaFree(chain->d_hist); cudaFree(chain->d_bq);
+  cudaFree(chain->d_sets); cudaFree(chain->d_set_kp4); cudaFree(chain->d_ctrl);
+  cudaFree(chain->d_in); cudaFree(chain->d_out);
+  if (chain->pin_in) cudaFreeHost(chain->pin_in);
+  if (chain->pin_out) cudaFreeHost(chain->pin_out);
+  for (cudaEvent_t ev : chain->pipe_ev) cudaEventDestroy(ev);
+  if (chain->ev0) cudaEventDestroy(chain->ev0);
+  if (chain->ev1) cudaEventDestroy(chain->ev1);
+  if (chain->own_stream) cudaStreamDestroy(chain->own_stream);
+  if (chain->copy_in) cudaStreamDestroy(chain->copy_in);
+  if (chain->copy_out) cudaStreamDestroy(chain->copy_out);
+  delete chain;
+}
+
+int msdr_chain_set_stream(msdr_chain *chain, void *cuda_stream)
+{
+  if (!chain) return MSDR_ERR_ARGUMENT;
+  CK(cudaSetDevice(chain->device));
+  CK(cudaStreamSynchronize(chain->stream));
+  chain->stream = cuda_stream ? (cudaStream_t)cuda_stream : chain->own_stream;
+  return MSDR_OK;
+}
+
+int msdr_chain_synchronize(msdr_chain *chain)
+{
+  if (!chain) return MSDR_ERR_ARGUMENT;
+  CK(cudaSetDevice(chain->device));
+  CK(cudaStreamSynchronize(chain->stream));
+  return MSDR_OK;
+}
+
+const char *msdr_last_error(const msdr_chain *chain) { return chain ? chain->err.c_str() : g_create_error.c_str(); }
+uint32_t msdr_chain_channels(const msdr_chain *chain) { return chain ? chain->C : 0; }
+uint64_t msdr_chain_launch_count(const msdr_chain *chain) { return chain ? chain->launches : 0; }
+
+int msdr_chain_set_mode(msdr_chain *chain, uint32_t ch0, uint32_t nch, int mode)
+{
+  if (!chain) return MSDR_ERR_ARGUMENT;
+  if (!range_ok(chain, ch0, nch) || mode < 0 || mode > 4) return fail(chain, MSDR_ERR_ARGUMENT, "set_mode: bad channel range or mode");
+  if (mode == MSDR_MODE_SYNCAM && !(chain->flags & MSDR_FLAG_AM_Q31))
+    return fail(chain, MSDR_ERR_UNSUPPORTED, "SYNCAM PLL demodulator (Minimal-SDR.ino:631-688) is not on the hot path; use MSDR_FLAG_AM_Q31 for the Teensy 3.2 envelope");
+  if (nch == 0) return MSDR_OK;
+  CK(cudaSetDevice(chain->device));
+  std::fill(chain->h_mode.begin() + ch0, chain->h_mode.begin() + ch0 + nch, (uint8_t)mode);
+  CK(cudaMemsetAsync(chain->d_mode + ch0, mode, nch, chain->stream));
+  return MSDR_OK;
+}
+
+int msdr_fir_init_q15(msdr_chain *chain, uint32_t ch0, uint32_t nch, uint16_t numTaps, const int16_t *cI, const int16_t *cQ)
+{
+  if (!chain) return MSDR_ERR_ARGUMENT;
+  if (numTaps & 1u) return fail(chain, MSDR_ERR_ARGUMENT, "arm_fir_init_q15: numTaps must be even (arm_fir_init_q15.c:93-96)");
+  if (!cI || !cQ || !range_ok(chain, ch0, nch)) return fail(chain, MSDR_ERR_ARGUMENT, "fir_init: bad arguments");
+  if (numTaps < 4 || numTaps > chain->max_taps) return fail(chain, MSDR_ERR_LENGTH, "fir_init: numTaps outside [4, max_taps of this chain]");
+  if (nch == 0) return MSDR_OK;
+  CK(cudaSetDevice(chain->device));
+  const int id = intern_set(chain, numTaps, cI, cQ);
+  if (id < 0) return id;
+  int st = assign_set(chain, ch0, nch, (uint32_t)id);
+  if (st != MSDR_OK) return st;
+  CK(cudaMemsetAsync(chain->d_hist + (size_t)ch0 * chain->H, 0, (size_t)nch * chain->H * sizeof(int16_t), chain->stream)); // init_FIR memset, .ino:902-903
+  return MSDR_OK;
+}
+
+int msdr_fir_set_coefficients(msdr_chain *chain, uint32_t ch0, uint32_t nch, const int16_t *cI, const int16_t *cQ)
+{
+  if (!chain) return MSDR_ERR_ARGUMENT;
+  if (!cI || !cQ || !range_ok(chain, ch0, nch) || nch == 0) return fail(chain, MSDR_ERR_ARGUMENT, "fir_set_coefficients: bad arguments");
+  const uint8_t cur = chain->h_set[ch0];
+  if (cur == 0xFF) return fail(chain, MSDR_ERR_NOT_INITIALISED, "fir_set_coefficients: FIR not initialised");
+  for (uint32_t c = ch0; c < ch0 + nch; ++c)
+    if (chain->h_set[c] != cur) return fail(chain, MSDR_ERR_ARGUMENT, "fir_set_coefficients: channels in the range do not share one table");
+  CK(cudaSetDevice(chain->device));
+  const uint32_t T = chain->sets[cur].T;
+  if (chain->sets[cur].users == nch) { // every user is in the range: rewrite in place, like the sketch's single table
+    chain->sets[cur].cI.assign(cI, cI + T);
+    chain->sets[cur].cQ.assign(cQ, cQ + T);
+    return upload_set(chain, cur);
+  }
+  const int id = intern_set(chain, T, cI, cQ);
+  if (id < 0) return id;
+  return assign_set(chain, ch0, nch, (uint32_t)id); // delay lines untouched
+}
+
+int msdr_biquad_set_coefficients(msdr_chain *chain, int object, uint32_t ch0, uint32_t nch, uint32_t stage, const int32_t *coef)
+{
+  if (!chain) return MSDR_ERR_ARGUMENT;
+  if (object < 0 || object >= MSDR_BIQUAD_OBJECTS || !coef || !range_ok(chain, ch0, nch))
+    return fail(chain, MSDR_ERR_ARGUMENT, "biquad_set_coefficients: bad arguments");
+  if (stage >= 4 || nch == 0) return MSDR_OK; // filter_biquad.cpp:86: silently ignored
+  CK(cudaSetDevice(chain->device));
+  CK(launch_bq_setcoef(chain->d_bq, chain->Cpad, object, ch0, nch, stage, coef, chain->stream));
+  chain->launches++;
+  return MSDR_OK;
+}
+
+int msdr_chain_update_device(msdr_chain *chain, const int16_t *d_in, int16_t *d_out, uint32_t n_blocks, size_t stride)
+{
+  if (!chain) return MSDR_ERR_ARGUMENT;
+  if (n_blocks == 0) return MSDR_OK;
+  const uint64_t L64 = (uint64_t)n_blocks * MSDR_BLOCK_SAMPLES;
+  if (!d_in || !d_out || L64 > stride || L64 > 0x7FFFFF00ull) return fail(chain, MSDR_ERR_ARGUMENT, "update: bad buffers / stride < n_blocks*128");
+  if (((uintptr_t)d_in & 15u) || ((uintptr_t)d_out & 15u) || (stride & 7u))
+    return fail(chain, MSDR_ERR_ARGUMENT, "update_device: buffers must be 16-byte aligned and stride a multiple of 8 samples");
+  if (chain->n_uninit) return fail(chain, MSDR_ERR_NOT_INITIALISED, "update: some channels have no FIR bound (call msdr_fir_init_q15)");
+  CK(cudaSetDevice(chain->device));
+
+  ChainParams p{};
+  p.in = d_in; p.out = d_out; p.stride = stride;
+  p.C = chain->C; p.Cpad = chain->Cpad; p.L = (uint32_t)L64; p.H = chain->H;
+  p.hist = chain->d_hist; p.bq = chain->d_bq; p.mode = chain->d_mode; p.setid = chain->d_set;
+  p.sets = chain->d_sets; p.set_kp4 = chain->d_set_kp4;
+  p.n_sets = (uint32_t)chain->sets.size(); p.set_stride_words = chain->set_stride_words;
+  p.ctrl = chain->d_ctrl;
+  p.am_q31 = (chain->flags & MSDR_FLAG_AM_Q31) ? 1u : 0u;
+  const uint32_t NG = (chain->C + kGroup - 1) / kGroup;
+  CK(cudaMemsetAsync(chain->d_ctrl, 0, (size_t)(1 + NG) * sizeof(int), chain->stream));
+  if (chain->timed) CK(cudaEventRecord(chain->ev0, chain->stream));
+  CK(launch_chain(p, chain->stream, chain->variant, &chain->last_info));
+  if (chain->timed) CK(cudaEventRecord(chain->ev1, chain->stream));
+  chain->launches++;
+  return MSDR_OK;
+}
+
+int msdr_chain_update(msdr_chain *chain, const int16_t *in, int16_t *out, uint32_t n_blocks, size_t stride)
+{
+  if (!chain) return MSDR_ERR_ARGUMENT;
+  if (n_blocks == 0) return MSDR_OK;
+  const size_t L = (size_t)n_blocks * MSDR_BLOCK_SAMPLES;
+  if (!in || !out || L > stride) return fail(chain, MSDR_ERR_ARGUMENT, "update: bad buffers / stride < n_blocks*128");
+  if (chain->n_uninit) return fail(chain, MSDR_ERR_NOT_INITIALISED, "update: some channels have no FIR bound (call msdr_fir_init_q15)");
+  CK(cudaSetDevice(chain->device));
+  // dense device staging [C][L]; rows are copied with their host stride
+  int st = ensure_stage(chain, (size_t)chain->C * L);
+  if (st != MSDR_OK) return st;
+  CK(cudaMemcpy2DAsync(chain->d_in, L * 2, in, stride * 2, L * 2, chain->C, cudaMemcpyHostToDevice, chain->stream));
+  st = msdr_chain_update_device(chain, chain->d_in, chain->d_out, n_blocks, L);
+  if (st != MSDR_OK) return st;
+  CK(cudaMemcpy2DAsync(out, stride * 2, chain->d_out, L * 2, L * 2, chain->C, cudaMemcpyDeviceToHost, chain->stream));
+  CK(cudaStreamSynchronize(chain->stream));
+  return MSDR_OK;
+}
+
+int msdr_chain_last_update_ms(msdr_chain *chain, float *ms)
+{
+  if (!chain || !ms) return MSDR_ERR_ARGUMENT;
+  if (!chain->timed) return fail(chain, MSDR_ERR_ARGUMENT, "enable with msdr_chain_set_option(chain, \"timing\", 1)");
+  CK(cudaSetDevice(chain->device));
+  CK(cudaEventSynchronize(chain->ev1));
+  CK(cudaEventElapsedTime(ms, chain->ev0, chain->ev1));
+  return MSDR_OK;
+}
+
+int msdr_chain_set_option(msdr_chain *chain, const char *key, int value)
+{
+  if (!chain || !key) return MSDR_ERR_ARGUMENT;
+  if (!strcmp(key, "variant")) { chain->variant = value; return MSDR_OK; }
+  if (!strcmp(key, "timing")) { chain->timed = value != 0; return MSDR_OK; }
+  if (!strcmp(key, "host_chunk_channels")) { chain->host_chunk_channels = (uint32_t)value; return MSDR_OK; }
+  return fail(chain, MSDR_ERR_ARGUMENT, std::string("unknown option ") + key);
+}
+
+int msdr_chain_get_state(msdr_chain *chain, uint32_t ch, msdr_channel_state *out)
+{
+  if (!chain || !out || ch >= chain->C) return MSDR_ERR_ARGUMENT;
+  CK(cudaSetDevice(chain->device));
+  CK(cudaStreamSynchronize(chain->stream));
+  memset(out, 0, sizeof(*out));
+  out->mode = chain->h_mode[ch];
+  const uint8_t sid = chain->h_set[ch];
+  out->fir_set = sid == 0xFF ? -1 : (int32_t)sid;
+  out->num_taps = sid == 0xFF ? 0 : chain->sets[sid].T;
+  std::vector<int16_t> h(chain->H);
+  CK(cudaMemcpy(h.data(), chain->d_hist + (size_t)ch * chain->H, chain->H * sizeof(int16_t), cudaMemcpyDeviceToHost));
+  if (out->num_taps) {
+    const uint32_t n = out->num_taps - 1;
+    memcpy(out->fir_history, h.data() + (chain->H - n), n * sizeof(int16_t));
+  }
+  int32_t bq[kBqWords];
+  CK(cudaMemcpy2D(bq, sizeof(int32_t), chain->d_bq + ch, (size_t)chain->Cpad * sizeof(int32_t), sizeof(int32_t), kBqWords, cudaMemcpyDeviceToHost));
+  memcpy(out->biquad_definition, bq, sizeof(bq));
+  return MSDR_OK;
+}
+
+int msdr_chain_set_state(msdr_chain *chain, uint32_t ch, const msdr_channel_state *in)
+{
+  if (!chain || !in || ch >= chain->C) return MSDR_ERR_ARGUMENT;
+  if (in->mode < 0 || in->mode > 4) return fail(chain, MSDR_ERR_ARGUMENT, "set_state: bad mode");
+  const uint8_t sid = chain->h_set[ch];
+  if (sid == 0xFF || chain->sets[sid].T != in->num_taps)
+    return fail(chain, MSDR_ERR_ARGUMENT, "set_state: bind the FIR (msdr_fir_init_q15) with the same tap count first");
+  CK(cudaSetDevice(chain->device));
+  CK(cudaStreamSynchronize(chain->stream));
+  int st = msdr_chain_set_mode(chain, ch, 1, in->mode);
+  if (st != MSDR_OK) return st;
+  std::vector<int16_t> h(chain->H, 0);
+  const uint32_t n = in->num_taps - 1;
+  memcpy(h.data() + (chain->H - n), in->fir_history, n * sizeof(int16_t));
+  CK(cudaMemcpy(chain->d_hist + (size_t)ch * chain->H, h.data(), chain->H * sizeof(int16_t), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy2D(chain->d_bq + ch, (size_t)chain->Cpad * sizeof(int32_t), in->biquad_definition, sizeof(int32_t), sizeof(int32_t), kBqWords,
+                  cudaMemcpyHostToDevice));
+  return MSDR_OK;
+}
+
+void *msdr_host_alloc(size_t bytes)
+{
+  void *p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+  return p;
+}
+void msdr_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+} // extern "C"
+
+// ---- stage-level operators ----------------------------------------------------------------------------
+
+namespace {
+struct DevBuf {
+  void *p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
+  template <class T> T *as() { return static_cast<T *>(p); }
+};
+int op_fail(cudaError_t e, const char *what) { g_create_error = std::string(what) + ": " + cudaGetErrorString(e); return MSDR_ERR_CUDA; }
+#define OPCK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return op_fail(e__, #call); } while (0)
+int op_begin(int device)
+{
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_create_error = "no CUDA device: this library has no CPU fallback"; return MSDR_ERR_CUDA; }
+  if (device < 0 || device >= ndev) return MSDR_ERR_ARGUMENT;
+  OPCK(cudaSetDevice(device));
+  return MSDR_OK;
+}
+} // namespace
+
+extern "C" {
+
+int msdr_op_mix_fs4(int device, const int16_t *in, int16_t *outI, int16_t *outQ, uint32_t rows, uint32_t n, size_t stride)
+{
+  if (!in || !outI || !outQ || (n & 3u) || n > stride) return MSDR_ERR_ARGUMENT;
+  int st = op_begin(device); if (st) return st;
+  DevBuf a, b, c;
+  const size_t bytes = (size_t)rows * n * 2;
+  OPCK(a.alloc(bytes)); OPCK(b.alloc(bytes)); OPCK(c.alloc(bytes));
+  OPCK(cudaMemcpy2D(a.p, (size_t)n * 2, in, stride * 2, (size_t)n * 2, rows, cudaMemcpyHostToDevice));
+  OPCK(launch_mix_fs4(a.as<int16_t>(), b.as<int16_t>(), c.as<int16_t>(), rows, n, n, nullptr));
+  OPCK(cudaMemcpy2D(outI, stride * 2, b.p, (size_t)n * 2, (size_t)n * 2, rows, cudaMemcpyDeviceToHost));
+  OPCK(cudaMemcpy2D(outQ, stride * 2, c.p, (size_t)n * 2, (size_t)n * 2, rows, cudaMemcpyDeviceToHost));
+  return MSDR_OK;
+}
+
+int msdr_op_fir_fast_q15(int device, uint16_t numTaps, const int16_t *coeffs, int16_t *history, const int16_t *in, int16_t *out, uint32_t rows,
+                         uint32_t n, size_t stride)
+{
+  if (numTaps & 1u) return MSDR_ERR_ARGUMENT; // arm_fir_init_q15.c:93-96
+  if (!coeffs || !in || !out || numTaps < 2 || n > stride) return MSDR_ERR_ARGUMENT;
+  int st = op_begin(device); if (st) return st;
+  DevBuf dc, dh, dh2, di, dout;
+  const size_t bytes = (size_t)rows * n * 2, hbytes = (size_t)rows * (numTaps - 1) * 2;
+  OPCK(dc.alloc(numTaps * 2)); OPCK(di.alloc(bytes)); OPCK(dout.alloc(bytes));
+  OPCK(cudaMemcpy(dc.p, coeffs, numTaps * 2, cudaMemcpyHostToDevice));
+  if (history) { OPCK(dh.alloc(hbytes)); OPCK(dh2.alloc(hbytes)); OPCK(cudaMemcpy(dh.p, history, hbytes, cudaMemcpyHostToDevice)); }
+  OPCK(cudaMemcpy2D(di.p, (size_t)n * 2, in, stride * 2, (size_t)n * 2, rows, cudaMemcpyHostToDevice));
+  OPCK(launch_fir_fast_q15(numTaps, dc.as<int16_t>(), history ? dh.as<int16_t>() : nullptr, history ? dh2.as<int16_t>() : nullptr, di.as<int16_t>(),
+                           dout.as<int16_t>(), rows, n, n, nullptr));
+  OPCK(cudaMemcpy2D(out, stride * 2, dout.p, (size_t)n * 2, (size_t)n * 2, rows, cudaMemcpyDeviceToHost));
+  if (history) OPCK(cudaMemcpy(history, dh2.p, hbytes, cudaMemcpyDeviceToHost));
+  return MSDR_OK;
+}
+
+int msdr_op_demod(int device, int kind, const int16_t *I, const int16_t *Q, int16_t *out, uint32_t rows, uint32_t n, size_t stride)
+{
+  if (!I || !Q || !out || kind < 0 || kind > 3 || n > stride) return MSDR_ERR_ARGUMENT;
+  int st = op_begin(device); if (st) return st;
+  DevBuf a, b, c;
+  const size_t bytes = (size_t)rows * n * 2;
+  OPCK(a.alloc(bytes)); OPCK(b.alloc(bytes)); OPCK(c.alloc(bytes));
+  OPCK(cudaMemcpy2D(a.p, (size_t)n * 2, I, stride * 2, (size_t)n * 2, rows, cudaMemcpyHostToDevice));
+  OPCK(cudaMemcpy2D(b.p, (size_t)n * 2, Q, stride * 2, (size_t)n * 2, rows, cudaMemcpyHostToDevice));
+  OPCK(launch_demod(kind, a.as<int16_t>(), b.as<int16_t>(), c.as<int16_t>(), rows, n, n, nullptr));
+  OPCK(cudaMemcpy2D(out, stride * 2, c.p, (size_t)n * 2, (size_t)n * 2, rows, cudaMemcpyDeviceToHost));
+  return MSDR_OK;
+}
+
+int msdr_op_biquad(int device, int32_t *definition, int16_t *data, uint32_t rows, uint32_t n, size_t stride)
+{
+  if (!definition || !data || (n & 1u) || n > stride) return MSDR_ERR_ARGUMENT;
+  int st = op_begin(device); if (st) return st;
+  DevBuf dd, dx;
+  const size_t n2 = (n + 7u) & ~7u; // keep rows 16-byte aligned
+  OPCK(dd.alloc((size_t)rows * 32 * 4)); OPCK(dx.alloc((size_t)rows * n2 * 2));
+  OPCK(cudaMemcpy(dd.p, definition, (size_t)rows * 32 * 4, cudaMemcpyHostToDevice));
+  OPCK(cudaMemcpy2D(dx.p, n2 * 2, data, stride * 2, (size_t)n * 2, rows, cudaMemcpyHostToDevice));
+  OPCK(launch_biquad(dd.as<int32_t>(), dx.as<int16_t>(), rows, n, n2, nullptr));
+  OPCK(cudaMemcpy2D(data, stride * 2, dx.p, n2 * 2, (size_t)n * 2, rows, cudaMemcpyDeviceToHost));
+  OPCK(cudaMemcpy(definition, dd.p, (size_t)rows * 32 * 4, cudaMemcpyDeviceToHost));
+  return MSDR_OK;
+}
+
+int msdr_op_freq_conv(int device, int dir, int pass, int16_t *I, int16_t *Q, const int16_t *oscI, const int16_t *oscQ, uint32_t rows, uint32_t n,
+                      size_t stride)
+{
+  if (!I || !Q || !oscI || !oscQ || n > stride) return MSDR_ERR_ARGUMENT;
+  int st = op_begin(device); if (st) return st;
+  if (!pass) return MSDR_OK; // freq_conv.cpp:49-56: inputs forwarded unchanged
+  DevBuf a, b, oi, oq;
+  const size_t bytes = (size_t)rows * n * 2;
+  OPCK(a.alloc(bytes)); OPCK(b.alloc(bytes)); OPCK(oi.alloc((size_t)n * 2)); OPCK(oq.alloc((size_t)n * 2));
+  OPCK(cudaMemcpy2D(a.p, (size_t)n * 2, I, stride * 2, (size_t)n * 2, rows, cudaMemcpyHostToDevice));
+  OPCK(cudaMemcpy2D(b.p, (size_t)n * 2, Q, stride * 2, (size_t)n * 2, rows, cudaMemcpyHostToDevice));
+  OPCK(cudaMemcpy(oi.p, oscI, (size_t)n * 2, cudaMemcpyHostToDevice));
+  OPCK(cudaMemcpy(oq.p, oscQ, (size_t)n * 2, cudaMemcpyHostToDevice));
+  OPCK(launch_freq_conv(dir, a.as<int16_t>(), b.as<int16_t>(), oi.as<int16_t>(), oq.as<int16_t>(), rows, n, n, nullptr));
+  OPCK(cudaMemcpy2D(I, stride * 2, a.p, (size_t)n * 2, (size_t)n * 2, rows, cudaMemcpyDeviceToHost));
+  OPCK(cudaMemcpy2D(Q, stride * 2, b.p, (size_t)n * 2, (size_t)n * 2, rows, cudaMemcpyDeviceToHost));
+  return MSDR_OK;
+}
+
+int msdr_op_sqrt_q31(int device, const int32_t *in, int32_t *out, int32_t *status, uint32_t n)
+{
+  if (!in || !out) return MSDR_ERR_ARGUMENT;
+  int st = op_begin(device); if (st) return st;
+  DevBuf a, b, c;
+  OPCK(a.alloc((size_t)n * 4)); OPCK(b.alloc((size_t)n * 4)); OPCK(c.alloc((size_t)n * 4));
+  OPCK(cudaMemcpy(a.p, in, (size_t)n * 4, cudaMemcpyHostToDevice));
+  OPCK(launch_sqrt_q31(a.as<int32_t>(), b.as<int32_t>(), c.as<int32_t>(), n, nullptr));
+  OPCK(cudaMemcpy(out, b.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  if (status) OPCK(cudaMemcpy(status, c.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  return MSDR_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,515 @@
+// msdr_chain_kernel.cu — K1: the fused receive chain for sm_100a.
+//
+//   int16 IF samples -> [fs/4 mix folded into tap selection] -> FIR pair (Q15, 32-bit wrapping accumulate)
+//   -> SSB sum / AM envelope -> biquad cascade (Q2.30 x int16, 14-bit error feedback) -> int16 audio
+//
+// Reference semantics: Minimal-SDR.ino:546-558 (mix), arm_fir_fast_q15.c:60-329 (FIR), Minimal-SDR.ino:589-628
+// (demod), filter_biquad.cpp:33-82 (biquad).  Bit-exact by construction, see DESIGN.md "Exactness".
+//
+// Structure (one persistent CTA per SM, warp-specialised, mbarrier pipelines):
+//
+//   warp 0        producer  claims (channel-group, time-segment) work items from a global counter and streams
+//                           their tiles HBM -> shared memory with cp.async.bulk (TMA engine), one 1-D bulk
+//                           copy per channel row covering the (T-1)-sample halo plus the tile.
+//   warps 1..NF   FIR       fold the fs/4 oscillator sign into the samples in place, then each warp takes one
+//                           channel row at a time: lane l computes 2R consecutive outputs of all four
+//                           polyphase sub-filters (I/Q x even/odd output phase) from a sliding register window,
+//                           taps broadcast from shared memory; epilogue does >>15, SSAT, demod; result goes to
+//                           a second shared buffer.
+//   warp NF+1     biquad    lane = channel: serial recurrence over the tile in shared memory, in place, state in
+//                           registers for the whole segment; then one bulk copy per row shared -> HBM.
+//
+// The only serial dependence across time is the biquad state.  Work items are ordered segment-major and the
+// biquad warp hands its state to the CTA that owns the next segment of the same channel group through global
+// memory + a release/acquire flag, so FIR work balances over all SMs for any channel count.
+#include "msdr_device.cuh"
+#include "msdr_internal.h"
+
+namespace msdr {
+
+struct TileDesc {
+  int grp;   // channel group
+  int seg;   // segment of the launch this tile belongs to
+  int t0;    // first sample of the tile (within the launch)
+  int len;   // samples (multiple of 128, <= TT)
+  uint32_t flags;
+  int pad[3];
+};
+enum : uint32_t { TF_SEG_FIRST = 1u, TF_SEG_LAST = 2u, TF_LAUNCH_LAST = 4u, TF_END = 0x80000000u };
+
+struct __align__(16) PipeCtrl {
+  uint64_t full[2];   // producer -> FIR : raw tile landed (tx bytes)
+  uint64_t empty[2];  // FIR -> producer : raw tile consumed
+  uint64_t dfull[2];  // FIR -> biquad   : demodulated tile ready
+  uint64_t dfree[2];  // biquad -> FIR   : demodulated tile buffer drained to HBM
+  TileDesc desc[2];
+  TileDesc ddesc[2];
+  int job_ctr[2];
+  int pad[2];
+  uint32_t rowinfo[2][kGroup]; // per row: setid | mode << 8 | kp4 << 16
+};
+static_assert(sizeof(PipeCtrl) <= 512, "PipeCtrl must fit its smem slot");
+constexpr uint32_t kCtrlBytes = 512;
+
+__host__ __device__ inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1u) / a * a; }
+
+size_t chain_smem_bytes(uint32_t H, uint32_t n_sets, uint32_t set_stride_words, int tile)
+{
+  const uint32_t sets_bytes = align_up(n_sets * set_stride_words * 4u, 128u);
+  const uint32_t raw_stage = kGroup * (H + (uint32_t)tile) * 2u;
+  const uint32_t d_stage = kGroup * ((uint32_t)tile / 2u + 4u) * 4u;
+  return (size_t)kCtrlBytes + sets_bytes + 2u * raw_stage + 2u * d_stage;
+}
+
+__device__ __forceinline__ void unpack4(const uint4 v, uint32_t *e, uint32_t *o)
+{
+  e[0] = (uint32_t)(int)(short)(v.x & 0xFFFFu); o[0] = (uint32_t)((int)v.x >> 16);
+  e[1] = (uint32_t)(int)(short)(v.y & 0xFFFFu); o[1] = (uint32_t)((int)v.y >> 16);
+  e[2] = (uint32_t)(int)(short)(v.z & 0xFFFFu); o[2] = (uint32_t)((int)v.z >> 16);
+  e[3] = (uint32_t)(int)(short)(v.w & 0xFFFFu); o[3] = (uint32_t)((int)v.w >> 16);
+}
+
+// One channel row of one tile: FIR pair + demod for lane's 2R output samples.
+//   rowW  : sign-folded raw samples of the row as words (even sample | odd sample << 16); word Hw is tile sample 0
+//   cf    : expanded taps of the row's coefficient set: per 4-tap chunk c, cf[4c+0..3] = A, B, C, D sub-filters
+//           A: I taps for odd outputs, B: I taps for even outputs, C: Q taps for odd outputs, D: Q taps for even
+//   With u = folded samples, ue[j] = u[2j], uo[j] = u[2j+1], output pair i = (n = 2i, 2i+1), KP = 4*kp4:
+//     accX[i] = sum_{d < KP} cX[d] * {ue|uo}[i - KP + 1 + d]      (exact mod 2^32, any order)
+// 4 taps x R output pairs x 4 sub-filters = 16R multiply-accumulates on a rotating register window.
+// The window holds W = R + 4 consecutive words; logical position x lives in physical register (x + 4*ROT) % W, so
+// sliding the window by one chunk (4 words) is a change of ROT, not a register move.
+template <int R, int ROT>
+__device__ __forceinline__ void fir_chunk(uint32_t (&e)[R + 4], uint32_t (&o)[R + 4], uint32_t (&aA)[R], uint32_t (&aB)[R], uint32_t (&aC)[R],
+                                          uint32_t (&aD)[R], const int4 *__restrict__ cf)
+{
+  constexpr int W = R + 4;
+  const int4 cA = cf[0], cB = cf[1], cC = cf[2], cD = cf[3];
+  const uint32_t ca[4] = {(uint32_t)cA.x, (uint32_t)cA.y, (uint32_t)cA.z, (uint32_t)cA.w};
+  const uint32_t cb[4] = {(uint32_t)cB.x, (uint32_t)cB.y, (uint32_t)cB.z, (uint32_t)cB.w};
+  const uint32_t cc[4] = {(uint32_t)cC.x, (uint32_t)cC.y, (uint32_t)cC.z, (uint32_t)cC.w};
+  const uint32_t cd[4] = {(uint32_t)cD.x, (uint32_t)cD.y, (uint32_t)cD.z, (uint32_t)cD.w};
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const uint32_t ev = e[(1 + r + t + 4 * ROT) % W], ov = o[(1 + r + t + 4 * ROT) % W];
+      aA[r] = ca[t] * ev + aA[r];
+      aB[r] = cb[t] * ev + aB[r];
+      aC[r] = cc[t] * ov + aC[r];
+      aD[r] = cd[t] * ov + aD[r];
+    }
+  }
+}
+
+// One channel row of one tile: FIR pair + demod for lane's 2R output samples.
+//   rowW  : sign-folded raw samples of the row as words (even sample | odd sample << 16); word Hw is tile sample 0
+//   cf    : expanded taps of the row's coefficient set: per 4-tap chunk c, cf[4c+0..3] = A, B, C, D sub-filters
+//           A: I taps for odd outputs, B: I taps for even outputs, C: Q taps for odd outputs, D: Q taps for even
+//   With u = folded samples, ue[j] = u[2j], uo[j] = u[2j+1], output pair i = (n = 2i, 2i+1), KP = 4*kp4:
+//     accX[i] = sum_{d < KP} cX[d] * {ue|uo}[i - KP + 1 + d]      (exact mod 2^32, any order)
+template <int R>
+__device__ __forceinline__ void fir_demod_row(const uint32_t *__restrict__ rowW, const int4 *__restrict__ cf, const int kp4, const int Hw,
+                                              const int lane, const int len, const int kind, uint32_t *__restrict__ drow)
+{
+  static_assert(R == 8, "the rotation schedule below assumes a 12-word window (3 chunks per turn)");
+  constexpr int W = R + 4;
+  const int i0 = lane * R;
+  if (2 * i0 >= len) return;
+  const uint4 *wp = reinterpret_cast<const uint4 *>(rowW + Hw + i0 - 4 * kp4);
+  uint32_t e[W], o[W];
+#pragma unroll
+  for (int g = 0; g < W / 4; ++g) unpack4(wp[g], e + 4 * g, o + 4 * g);
+  wp += W / 4;
+  uint32_t aA[R], aB[R], aC[R], aD[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) aA[r] = aB[r] = aC[r] = aD[r] = 0u;
+
+  // chunk c consumes window rotation c % 3 and then refills the 4 slots it vacated with words for chunk c + 1;
+  // the refill after the very last chunk reads 4 words past the lane's window (still inside the row buffer) and is unused.
+  int c = 0;
+#pragma unroll 1
+  for (; c + 3 <= kp4; c += 3) {
+    fir_chunk<R, 0>(e, o, aA, aB, aC, aD, cf + 4 * c);
+    unpack4(wp[0], e + 0, o + 0);
+    fir_chunk<R, 1>(e, o, aA, aB, aC, aD, cf + 4 * c + 4);
+    unpack4(wp[1], e + 4, o + 4);
+    fir_chunk<R, 2>(e, o, aA, aB, aC, aD, cf + 4 * c + 8);
+    unpack4(wp[2], e + 8, o + 8);
+    wp += 3;
+  }
+  if (c < kp4) {
+    fir_chunk<R, 0>(e, o, aA, aB, aC, aD, cf + 4 * c);
+    if (c + 1 < kp4) {
+      unpack4(wp[0], e + 0, o + 0);
+      fir_chunk<R, 1>(e, o, aA, aB, aC, aD, cf + 4 * c + 4);
+    }
+  }
+
+  // arm_fir_fast_q15.c:234-238: acc >> 15, SSAT16; then the demodulation switch (Minimal-SDR.ino:589-628)
+  uint32_t outw[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int Io = ssat16((int)aA[r] >> 15), Ie = ssat16((int)aB[r] >> 15);
+    const int Qo = ssat16((int)aC[r] >> 15), Qe = ssat16((int)aD[r] >> 15);
+    const int se = demod_sample(kind, Ie, Qe), so = demod_sample(kind, Io, Qo);
+    outw[r] = ((uint32_t)se & 0xFFFFu) | ((uint32_t)so << 16);
+  }
+  uint4 *dp = reinterpret_cast<uint4 *>(drow + i0);
+#pragma unroll
+  for (int g = 0; g < R / 4; ++g) dp[g] = make_uint4(outw[4 * g], outw[4 * g + 1], outw[4 * g + 2], outw[4 * g + 3]);
+}
+
+__device__ __forceinline__ int demod_kind_of(int mode, uint32_t am_q31)
+{
+  // Minimal-SDR.ino:589-628: LSB, USB; AM/CW (+SYNCAM on Teensy 3.2) envelope
+  if (mode == 2) return 0;
+  if (mode == 3) return 1;
+  if (mode == 0) return 3;
+  return am_q31 ? 3 : 2;
+}
+
+// two samples (one packed word) through NS fused stages; values carried as v << 16
+template <int NS>
+__device__ __forceinline__ uint32_t bq_word(BqStage (&st)[NS], uint32_t w)
+{
+  int xe = (int)(w << 16), xo = (int)(w & 0xFFFF0000u);
+#pragma unroll
+  for (int k = 0; k < NS; ++k) xe = bq_step(st[k], xe);
+#pragma unroll
+  for (int k = 0; k < NS; ++k) xo = bq_step(st[k], xo);
+  return __byte_perm((uint32_t)xe, (uint32_t)xo, 0x7632);
+}
+
+__device__ __forceinline__ void bq_load_stage(BqStage &s, uint32_t &flag, const int32_t *__restrict__ bq, uint32_t Cpad, int obj, int stage, uint32_t ch)
+{
+  const int32_t *b = bq + (size_t)((obj * 4 + stage) * 8) * Cpad + ch;
+  s.b0 = __ldcg(b + 0 * (size_t)Cpad);
+  s.b1 = __ldcg(b + 1 * (size_t)Cpad);
+  s.b2 = __ldcg(b + 2 * (size_t)Cpad);
+  s.a1 = __ldcg(b + 3 * (size_t)Cpad);
+  s.a2 = __ldcg(b + 4 * (size_t)Cpad);
+  bq_unpack_hist((uint32_t)__ldcg(b + 5 * (size_t)Cpad), s.x1, s.x2);
+  bq_unpack_hist((uint32_t)__ldcg(b + 6 * (size_t)Cpad), s.y1, s.y2);
+  const uint32_t w7 = (uint32_t)__ldcg(b + 7 * (size_t)Cpad);
+  s.res = (int)(w7 & 0x3FFFu); // filter_biquad.cpp:52
+  flag = w7 & 0x80000000u;
+}
+__device__ __forceinline__ void bq_store_stage(const BqStage &s, uint32_t flag, int32_t *__restrict__ bq, uint32_t Cpad, int obj, int stage, uint32_t ch)
+{
+  int32_t *b = bq + (size_t)((obj * 4 + stage) * 8) * Cpad + ch;
+  b[5 * (size_t)Cpad] = (int32_t)bq_pack_hist(s.x1, s.x2);
+  b[6 * (size_t)Cpad] = (int32_t)bq_pack_hist(s.y1, s.y2);
+  b[7 * (size_t)Cpad] = (int32_t)((uint32_t)s.res | flag); // filter_biquad.cpp:75-78
+}
+
+template <int TT, int NF>
+__global__ void __launch_bounds__((NF + 2) * 32, 1) chain_kernel(const ChainParams p)
+{
+  constexpr int R = TT / 64;      // output pairs per lane
+  constexpr int DW = TT / 2 + 4;  // demod-buffer row pitch in words (== 4 mod 32: conflict-free LDS.128 by row)
+  extern __shared__ __align__(128) unsigned char smem[];
+  PipeCtrl *pc = reinterpret_cast<PipeCtrl *>(smem);
+  int32_t *s_sets = reinterpret_cast<int32_t *>(smem + kCtrlBytes);
+  const uint32_t sets_words = p.n_sets * p.set_stride_words;
+  const uint32_t RS = p.H + TT; // raw row pitch, samples
+  unsigned char *raw_base = smem + kCtrlBytes + align_up(sets_words * 4u, 128u);
+  const uint32_t raw_stage = kGroup * RS * 2u;
+  unsigned char *d_base = raw_base + 2u * raw_stage;
+  constexpr uint32_t d_stage = kGroup * DW * 4u;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&pc->full[s], 1);
+      mbar_init(&pc->empty[s], NF);
+      mbar_init(&pc->dfull[s], NF);
+      mbar_init(&pc->dfree[s], 1);
+    }
+    mbar_fence_init();
+  }
+  for (uint32_t i = threadIdx.x; i < sets_words; i += blockDim.x) s_sets[i] = p.sets[i];
+  __syncthreads();
+
+  const int Hw = (int)(p.H >> 1);
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ producer
+    uint32_t it = 0;
+    for (;;) {
+      int item = 0;
+      if (lane == 0) item = atomicAdd(&p.ctrl[0], 1);
+      item = __shfl_sync(0xffffffffu, item, 0);
+      if (item >= (int)p.n_items) break;
+      const int seg = item / (int)p.NG, grp = item - seg * (int)p.NG; // segment-major order
+      const int tile_begin = seg * (int)p.TPS;
+      const int tile_end = min(tile_begin + (int)p.TPS, (int)p.NT);
+      const int nrows = min(kGroup, (int)p.C - grp * kGroup);
+      const uint32_t ch = (uint32_t)(grp * kGroup + lane);
+      uint32_t rinfo = 0;
+      if (lane < nrows) {
+        const uint32_t set = p.setid[ch];
+        rinfo = set | ((uint32_t)p.mode[ch] << 8) | (p.set_kp4[set] << 16);
+      }
+      for (int tile = tile_begin; tile < tile_end; ++tile, ++it) {
+        const int s = it & 1;
+        const uint32_t ph = (it >> 1) & 1u;
+        mbar_wait(&pc->empty[s], ph ^ 1u);
+        const int t0 = tile * TT;
+        const int len = min(TT, (int)p.L - t0);
+        pc->rowinfo[s][lane] = rinfo;
+        const uint32_t row_bytes = (p.H + (uint32_t)len) * 2u;
+        if (lane == 0) {
+          TileDesc td;
+          td.grp = grp; td.seg = seg; td.t0 = t0; td.len = len;
+          td.flags = (tile == tile_begin ? TF_SEG_FIRST : 0u) | (tile + 1 == tile_end ? TF_SEG_LAST : 0u) |
+                     (tile + 1 == (int)p.NT ? TF_LAUNCH_LAST : 0u);
+          td.pad[0] = td.pad[1] = td.pad[2] = 0;
+          pc->desc[s] = td;
+          pc->job_ctr[s] = 0;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive_expect_tx(&pc->full[s], (uint32_t)nrows * row_bytes);
+        __syncwarp();
+        if (lane < nrows) {
+          int16_t *dst = reinterpret_cast<int16_t *>(raw_base + (uint32_t)s * raw_stage) + (uint32_t)lane * RS;
+          if ((uint32_t)t0 >= p.H) {
+            bulk_g2s(dst, p.in + (size_t)ch * p.stride + (size_t)(t0 - (int)p.H), row_bytes, &pc->full[s]);
+          } else { // halo (partly) from the carried history
+            const uint32_t nh = p.H - (uint32_t)t0;
+            bulk_g2s(dst, p.hist + (size_t)ch * p.H + (size_t)t0, nh * 2u, &pc->full[s]);
+            bulk_g2s(dst + nh, p.in + (size_t)ch * p.stride, (uint32_t)(t0 + len) * 2u, &pc->full[s]);
+          }
+        }
+      }
+    }
+    { // end marker travels through the same ring
+      const int s = it & 1;
+      const uint32_t ph = (it >> 1) & 1u;
+      mbar_wait(&pc->empty[s], ph ^ 1u);
+      if (lane == 0) {
+        pc->desc[s].flags = TF_END;
+        mbar_arrive(&pc->full[s]);
+      }
+    }
+  } else if (warp <= NF) {
+    // ------------------------------------------------------------------ FIR + demod warps
+    const int ftid = (warp - 1) * 32 + lane;
+    for (uint32_t it = 0;; ++it) {
+      const int s = it & 1;
+      const uint32_t ph = (it >> 1) & 1u;
+      mbar_wait(&pc->full[s], ph);
+      const TileDesc td = pc->desc[s];
+      if (td.flags & TF_END) {
+        mbar_wait(&pc->dfree[s], ph ^ 1u);
+        if (ftid == 0) pc->ddesc[s] = td;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&pc->dfull[s]);
+        break;
+      }
+      const int nrows = min(kGroup, (int)p.C - td.grp * kGroup);
+      uint32_t *rawW = reinterpret_cast<uint32_t *>(raw_base + (uint32_t)s * raw_stage);
+      // fold the fs/4 oscillator sign: samples with n % 4 in {2,3} are negated (Minimal-SDR.ino:550,555),
+      // i.e. every odd word of the row
+      {
+        const int q4 = (int)((p.H + (uint32_t)td.len) >> 3); // uint4 per row
+        for (int idx = ftid; idx < nrows * q4; idx += NF * 32) {
+          const int r = idx / q4, c4 = idx - r * q4;
+          uint4 *pw = reinterpret_cast<uint4 *>(rawW + (uint32_t)r * (RS >> 1)) + c4;
+          uint4 v = *pw;
+          v.y = neg16x2(v.y);
+          v.w = neg16x2(v.w);
+          *pw = v;
+        }
+      }
+      named_bar_sync(1, NF * 32);
+      mbar_wait(&pc->dfree[s], ph ^ 1u);
+      if (ftid == 0) pc->ddesc[s] = td;
+      uint32_t *dW = reinterpret_cast<uint32_t *>(d_base + (uint32_t)s * d_stage);
+      for (;;) {
+        int job = 0;
+        if (lane == 0) job = atomicAdd(&pc->job_ctr[s], 1);
+        job = __shfl_sync(0xffffffffu, job, 0);
+        if (job >= nrows) break;
+        const uint32_t ri = pc->rowinfo[s][job];
+        const uint32_t set = ri & 0xFFu;
+        const int kind = demod_kind_of((int)((ri >> 8) & 0xFFu), p.am_q31);
+        const int4 *cf = reinterpret_cast<const int4 *>(s_sets + set * p.set_stride_words);
+        fir_demod_row<R>(rawW + (uint32_t)job * (RS >> 1), cf, (int)(ri >> 16), Hw, lane, td.len, kind, dW + (uint32_t)job * DW);
+      }
+      fence_proxy_async_smem(); // raw[s] was rewritten through the generic proxy; its next writer is the TMA engine
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&pc->dfull[s]);
+        mbar_arrive(&pc->empty[s]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ biquad warp (lane = channel)
+    int *flags = p.ctrl + 1;
+    BqStage st[2];
+    uint32_t fl[2] = {0u, 0u};
+    int nst0 = 1, nst1 = 1;
+    bool fast = true;
+    for (uint32_t it = 0;; ++it) {
+      const int s = it & 1;
+      const uint32_t ph = (it >> 1) & 1u;
+      mbar_wait(&pc->dfull[s], ph);
+      const TileDesc td = pc->ddesc[s];
+      if (td.flags & TF_END) break;
+      const uint32_t ch = (uint32_t)(td.grp * kGroup + lane);
+      const bool active = ch < p.C;
+      uint32_t *drow = reinterpret_cast<uint32_t *>(d_base + (uint32_t)s * d_stage) + (uint32_t)lane * DW;
+
+      if (td.flags & TF_SEG_FIRST) {
+        if (td.seg > 0) { // state hand-off from the CTA that ran the previous segment of this group
+          if (lane == 0) {
+            uint32_t spins = 0;
+            while (ld_acquire_gpu(flags + td.grp) < td.seg) {
+              __nanosleep(64);
+              if (++spins > (1u << 24)) __trap();
+            }
+          }
+          __syncwarp();
+        }
+        nst0 = nst1 = 1;
+        if (active) {
+          // stages run while bit31 of word 7 says another follows (filter_biquad.cpp:75,79)
+          for (int k = 0; k < 3 && (nst0 == k + 1); ++k)
+            if ((uint32_t)__ldcg(p.bq + (size_t)((0 * 4 + k) * 8 + 7) * p.Cpad + ch) & 0x80000000u) nst0 = k + 2;
+          for (int k = 0; k < 3 && (nst1 == k + 1); ++k)
+            if ((uint32_t)__ldcg(p.bq + (size_t)((1 * 4 + k) * 8 + 7) * p.Cpad + ch) & 0x80000000u) nst1 = k + 2;
+        }
+        fast = __all_sync(0xffffffffu, nst0 == 1 && nst1 == 1);
+        if (fast && active) {
+          bq_load_stage(st[0], fl[0], p.bq, p.Cpad, 0, 0, ch);
+          bq_load_stage(st[1], fl[1], p.bq, p.Cpad, 1, 0, ch);
+        }
+      }
+
+      if (fast) {
+        if (active) {
+          uint4 *dp = reinterpret_cast<uint4 *>(drow);
+#pragma unroll 1
+          for (int q = 0; q < (td.len >> 3); ++q) {
+            uint4 v = dp[q];
+            v.x = bq_word<2>(st, v.x);
+            v.y = bq_word<2>(st, v.y);
+            v.z = bq_word<2>(st, v.z);
+            v.w = bq_word<2>(st, v.w);
+            dp[q] = v;
+          }
+        }
+      } else {
+        // generic cascade: stage-major over the tile like the reference (filter_biquad.cpp:44-79)
+        for (int obj = 0; obj < 2; ++obj) {
+          const int myn = obj ? nst1 : nst0;
+          for (int k = 0; k < 4; ++k) {
+            const bool has = active && k < myn;
+            if (!__any_sync(0xffffffffu, has)) break;
+            if (has) {
+              BqStage g[1];
+              uint32_t gf;
+              bq_load_stage(g[0], gf, p.bq, p.Cpad, obj, k, ch);
+              uint4 *dp = reinterpret_cast<uint4 *>(drow);
+#pragma unroll 1
+              for (int q = 0; q < (td.len >> 3); ++q) {
+                uint4 v = dp[q];
+                v.x = bq_word<1>(g, v.x);
+                v.y = bq_word<1>(g, v.y);
+                v.z = bq_word<1>(g, v.z);
+                v.w = bq_word<1>(g, v.w);
+                dp[q] = v;
+              }
+              bq_store_stage(g[0], gf, p.bq, p.Cpad, obj, k, ch);
+            }
+          }
+        }
+      }
+
+      // drain the finished tile to HBM: one bulk copy per channel row
+      fence_proxy_async_smem();
+      if (active) bulk_s2g(p.out + (size_t)ch * p.stride + (size_t)td.t0, drow, (uint32_t)td.len * 2u);
+      bulk_commit();
+      if (it > 0) { // the previous tile's buffer is free once its copy has finished reading shared memory
+        bulk_wait_read<1>();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&pc->dfree[s ^ 1]);
+      }
+
+      if (td.flags & TF_SEG_LAST) {
+        if (fast && active) {
+          bq_store_stage(st[0], fl[0], p.bq, p.Cpad, 0, 0, ch);
+          bq_store_stage(st[1], fl[1], p.bq, p.Cpad, 1, 0, ch);
+        }
+        if (td.flags & TF_LAUNCH_LAST) {
+          // carry the last H raw samples: hist <- tail of (hist || in[0..L))
+          const int nrows = min(kGroup, (int)p.C - td.grp * kGroup);
+          const uint32_t hq = p.H >> 3; // uint4 per history row (<= 33)
+          for (int r = 0; r < nrows; ++r) {
+            const size_t c = (size_t)(td.grp * kGroup + r);
+            uint4 *hrow = reinterpret_cast<uint4 *>(p.hist + c * p.H);
+            const uint4 *irow = reinterpret_cast<const uint4 *>(p.in + c * p.stride);
+            uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
+            const uint32_t i0 = (uint32_t)lane, i1 = (uint32_t)lane + 32u;
+            if (p.L >= p.H) {
+              const uint4 *src = irow + ((p.L - p.H) >> 3);
+              if (i0 < hq) v0 = src[i0];
+              if (i1 < hq) v1 = src[i1];
+            } else {
+              const uint32_t lq = p.L >> 3, keep = hq - lq; // keep = old entries that survive
+              if (i0 < hq) v0 = (i0 < keep) ? __ldcg(hrow + i0 + lq) : irow[i0 - keep];
+              if (i1 < hq) v1 = (i1 < keep) ? __ldcg(hrow + i1 + lq) : irow[i1 - keep];
+            }
+            __syncwarp();
+            if (i0 < hq) hrow[i0] = v0;
+            if (i1 < hq) hrow[i1] = v1;
+          }
+        }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) st_release_gpu(flags + td.grp, td.seg + 1);
+      }
+    }
+    bulk_wait<0>();
+  }
+}
+
+cudaError_t launch_chain(const ChainParams &p_in, cudaStream_t stream, int variant, ChainLaunchInfo *info)
+{
+  (void)variant;
+  constexpr int TT = 512, NF = 8;
+  ChainParams p = p_in;
+  int dev = 0, sms = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) return e;
+
+  p.NG = (p.C + kGroup - 1) / kGroup;
+  p.NT = (p.L + TT - 1) / TT;
+  // enough work items to balance the SMs, never finer than one tile
+  uint32_t S = (8u * (uint32_t)sms + p.NG - 1) / p.NG;
+  if (S > p.NT) S = p.NT;
+  if (S < 1) S = 1;
+  p.TPS = (p.NT + S - 1) / S;
+  p.S = (p.NT + p.TPS - 1) / p.TPS;
+  p.n_items = p.NG * p.S;
+
+  const size_t smem = chain_smem_bytes(p.H, p.n_sets, p.set_stride_words, TT);
+  auto kern = chain_kernel<TT, NF>;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (NF + 2) * 32, smem);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+  // every CTA must be resident: the biquad hand-off spins on flags owned by other CTAs
+  uint32_t grid = (uint32_t)sms * (uint32_t)per_sm;
+  if (grid > p.n_items) grid = p.n_items;
+  if (info) { info->grid = (int)grid; info->block = (NF + 2) * 32; info->smem = smem; info->tile = TT; }
+  kern<<<grid, (NF + 2) * 32, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+} // namespace msdr

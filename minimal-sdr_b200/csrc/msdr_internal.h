@@ -1,0 +1,63 @@
+// msdr_internal.h — host/device shared declarations (not part of the public ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace msdr {
+
+constexpr int kGroup = 32;            // channels per work group (one biquad lane each)
+constexpr int kBqWords = 64;          // 2 objects x 4 stages x 8 words (filter_biquad.h:152)
+
+// taps per polyphase sub-filter, padded: KP = roundup4(T/2 + 1)
+inline __host__ __device__ uint32_t kp_of_taps(uint32_t T) { return ((T / 2u + 1u) + 3u) & ~3u; }
+// raw-sample halo carried in front of each tile: H = roundup8(2*KP - 2) >= T - 1
+inline __host__ __device__ uint32_t hist_of_kp(uint32_t KP) { return ((2u * KP - 2u) + 7u) & ~7u; }
+
+struct ChainParams {
+  const int16_t *in;      // [C][stride]
+  int16_t *out;           // [C][stride]
+  size_t stride;          // samples
+  uint32_t C;             // channels
+  uint32_t Cpad;          // row pitch of the SoA state arrays (multiple of 32)
+  uint32_t L;             // samples per channel in this launch (multiple of 128)
+  uint32_t H;             // history / halo length in samples (multiple of 8)
+  int16_t *hist;          // [C][H]   last H raw ADC samples per channel
+  int32_t *bq;            // [64][Cpad] biquad definition words, SoA
+  const uint8_t *mode;    // [C] msdr_mode
+  const uint8_t *setid;   // [C] FIR coefficient-set id
+  const int32_t *sets;    // [n_sets][set_stride_words] expanded polyphase taps
+  const uint32_t *set_kp4; // [n_sets] number of 4-tap chunks
+  uint32_t n_sets;
+  uint32_t set_stride_words;
+  uint32_t NG;            // channel groups
+  uint32_t NT;            // tiles per channel in this launch
+  uint32_t TPS;           // tiles per segment
+  uint32_t S;             // segments per group
+  uint32_t n_items;       // NG * S
+  int *ctrl;              // [0] work counter, [1 + g] segments completed for group g
+  uint32_t am_q31;
+};
+
+struct ChainLaunchInfo {
+  int grid, block;
+  size_t smem;
+  int tile;
+};
+
+// Fused mix + FIR pair + demod + biquad cascade (K1). variant: 0 = default.
+cudaError_t launch_chain(const ChainParams &p, cudaStream_t stream, int variant, ChainLaunchInfo *info);
+size_t chain_smem_bytes(uint32_t H, uint32_t n_sets, uint32_t set_stride_words, int tile);
+
+// stage-level kernels on device buffers
+cudaError_t launch_mix_fs4(const int16_t *in, int16_t *I, int16_t *Q, uint32_t rows, uint32_t n, size_t stride, cudaStream_t s);
+cudaError_t launch_fir_fast_q15(uint32_t T, const int16_t *coef, const int16_t *hist_in, int16_t *hist_out, const int16_t *in, int16_t *out,
+                                uint32_t rows, uint32_t n, size_t stride, cudaStream_t s);
+cudaError_t launch_demod(int kind, const int16_t *I, const int16_t *Q, int16_t *out, uint32_t rows, uint32_t n, size_t stride, cudaStream_t s);
+cudaError_t launch_biquad(int32_t *definition, int16_t *data, uint32_t rows, uint32_t n, size_t stride, cudaStream_t s);
+cudaError_t launch_freq_conv(int dir, int16_t *I, int16_t *Q, const int16_t *oscI, const int16_t *oscQ, uint32_t rows, uint32_t n, size_t stride,
+                             cudaStream_t s);
+cudaError_t launch_sqrt_q31(const int32_t *in, int32_t *out, int32_t *status, uint32_t n, cudaStream_t s);
+cudaError_t launch_bq_setcoef(int32_t *bq, uint32_t Cpad, int object, uint32_t ch0, uint32_t nch, uint32_t stage, const int32_t coef[5], cudaStream_t s);
+
+} // namespace msdr
