@@ -112,6 +112,11 @@ int msdr_chain_update(msdr_chain *chain, const int16_t *in, int16_t *out, uint32
  * of 8 samples; in and out may not overlap. */
 int msdr_chain_update_device(msdr_chain *chain, const int16_t *d_in, int16_t *d_out, uint32_t n_blocks, size_t stride);
 
+/* Same for the channel sub-range [ch0, ch0+nch) only: d_in/d_out hold nch rows (row r = channel ch0 + r).
+ * Lets a caller stream channel shards through the device independently (msdr_chain_update does exactly that). */
+int msdr_chain_update_range_device(msdr_chain *chain, uint32_t ch0, uint32_t nch, const int16_t *d_in, int16_t *d_out, uint32_t n_blocks,
+                                   size_t stride);
+
 /* Device time of the last update in milliseconds (CUDA events), the analogue of the reference's
  * micros()-around-demodulation() load figure (Minimal-SDR.ino:533,774; :415-432). Synchronises. */
 int msdr_chain_last_update_ms(msdr_chain *chain, float *ms);

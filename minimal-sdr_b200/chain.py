@@ -144,6 +144,11 @@ class ReceiveChain:
         """Device pointers (ints), asynchronous on the chain's stream."""
         return self._ck(self._L.msdr_chain_update_device(self.h, C.c_void_p(int(d_in)), C.c_void_p(int(d_out)), int(n_blocks), int(stride)))
 
+    def update_range_device(self, ch0, nch, d_in, d_out, n_blocks, stride):
+        """Only channels [ch0, ch0+nch); the buffers hold nch rows."""
+        return self._ck(self._L.msdr_chain_update_range_device(self.h, int(ch0), int(nch), C.c_void_p(int(d_in)), C.c_void_p(int(d_out)),
+                                                               int(n_blocks), int(stride)))
+
     def synchronize(self):
         return self._ck(self._L.msdr_chain_synchronize(self.h))
 

@@ -325,11 +325,13 @@ int msdr_biquad_set_coefficients(msdr_chain *chain, int object, uint32_t ch0, ui
   return MSDR_OK;
 }
 
-int msdr_chain_update_device(msdr_chain *chain, const int16_t *d_in, int16_t *d_out, uint32_t n_blocks, size_t stride)
+int msdr_chain_update_range_device(msdr_chain *chain, uint32_t ch0, uint32_t nch, const int16_t *d_in, int16_t *d_out, uint32_t n_blocks,
+                                   size_t stride)
 {
   if (!chain) return MSDR_ERR_ARGUMENT;
-  if (n_blocks == 0) return MSDR_OK;
+  if (n_blocks == 0 || nch == 0) return MSDR_OK;
   const uint64_t L64 = (uint64_t)n_blocks * MSDR_BLOCK_SAMPLES;
+  if (!range_ok(chain, ch0, nch)) return fail(chain, MSDR_ERR_ARGUMENT, "update: bad channel range");
   if (!d_in || !d_out || L64 > stride || L64 > 0x7FFFFF00ull) return fail(chain, MSDR_ERR_ARGUMENT, "update: bad buffers / stride < n_blocks*128");
   if (((uintptr_t)d_in & 15u) || ((uintptr_t)d_out & 15u) || (stride & 7u))
     return fail(chain, MSDR_ERR_ARGUMENT, "update_device: buffers must be 16-byte aligned and stride a multiple of 8 samples");
@@ -338,13 +340,13 @@ int msdr_chain_update_device(msdr_chain *chain, const int16_t *d_in, int16_t *d_
 
   ChainParams p{};
   p.in = d_in; p.out = d_out; p.stride = stride;
-  p.C = chain->C; p.Cpad = chain->Cpad; p.L = (uint32_t)L64; p.H = chain->H;
+  p.C = nch; p.ch0 = ch0; p.Cpad = chain->Cpad; p.L = (uint32_t)L64; p.H = chain->H;
   p.hist = chain->d_hist; p.bq = chain->d_bq; p.mode = chain->d_mode; p.setid = chain->d_set;
   p.sets = chain->d_sets; p.set_kp4 = chain->d_set_kp4;
   p.n_sets = (uint32_t)chain->sets.size(); p.set_stride_words = chain->set_stride_words;
   p.ctrl = chain->d_ctrl;
   p.am_q31 = (chain->flags & MSDR_FLAG_AM_Q31) ? 1u : 0u;
-  const uint32_t NG = (chain->C + kGroup - 1) / kGroup;
+  const uint32_t NG = (nch + kGroup - 1) / kGroup;
   CK(cudaMemsetAsync(chain->d_ctrl, 0, (size_t)(1 + NG) * sizeof(int), chain->stream));
   if (chain->timed) CK(cudaEventRecord(chain->ev0, chain->stream));
   CK(launch_chain(p, chain->stream, chain->variant, &chain->last_info));
@@ -353,6 +355,14 @@ int msdr_chain_update_device(msdr_chain *chain, const int16_t *d_in, int16_t *d_
   return MSDR_OK;
 }
 
+int msdr_chain_update_device(msdr_chain *chain, const int16_t *d_in, int16_t *d_out, uint32_t n_blocks, size_t stride)
+{
+  if (!chain) return MSDR_ERR_ARGUMENT;
+  return msdr_chain_update_range_device(chain, 0, chain->C, d_in, d_out, n_blocks, stride);
+}
+
+// Host buffers: channels are cut into chunks that flow through a 3-slot device ring — H2D copy (stream copy_in),
+// fused kernel (chain stream), D2H copy (stream copy_out) — so PCIe traffic in both directions overlaps the kernels.
 int msdr_chain_update(msdr_chain *chain, const int16_t *in, int16_t *out, uint32_t n_blocks, size_t stride)
 {
   if (!chain) return MSDR_ERR_ARGUMENT;
@@ -361,13 +371,42 @@ int msdr_chain_update(msdr_chain *chain, const int16_t *in, int16_t *out, uint32
   if (!in || !out || L > stride) return fail(chain, MSDR_ERR_ARGUMENT, "update: bad buffers / stride < n_blocks*128");
   if (chain->n_uninit) return fail(chain, MSDR_ERR_NOT_INITIALISED, "update: some channels have no FIR bound (call msdr_fir_init_q15)");
   CK(cudaSetDevice(chain->device));
-  // dense device staging [C][L]; rows are copied with their host stride
-  int st = ensure_stage(chain, (size_t)chain->C * L);
+  constexpr int kSlots = 3;
+  uint32_t Cc = chain->host_chunk_channels;
+  if (Cc == 0) { // ~32 MiB per chunk and direction
+    Cc = (uint32_t)std::max<size_t>(kGroup, ((size_t)32 << 20) / (L * 2) / kGroup * kGroup);
+  }
+  Cc = std::min(Cc, (chain->C + kGroup - 1) / kGroup * kGroup);
+  Cc = std::max<uint32_t>(kGroup, Cc / kGroup * kGroup);
+  const size_t slot_samples = (size_t)Cc * L;
+  int st = ensure_stage(chain, slot_samples * kSlots);
   if (st != MSDR_OK) return st;
-  CK(cudaMemcpy2DAsync(chain->d_in, L * 2, in, stride * 2, L * 2, chain->C, cudaMemcpyHostToDevice, chain->stream));
-  st = msdr_chain_update_device(chain, chain->d_in, chain->d_out, n_blocks, L);
-  if (st != MSDR_OK) return st;
-  CK(cudaMemcpy2DAsync(out, stride * 2, chain->d_out, L * 2, L * 2, chain->C, cudaMemcpyDeviceToHost, chain->stream));
+  if (chain->pipe_ev.empty()) {
+    chain->pipe_ev.resize(3 * kSlots);
+    for (auto &ev : chain->pipe_ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  }
+  cudaEvent_t *ev_h2d = chain->pipe_ev.data(), *ev_k = ev_h2d + kSlots, *ev_d2h = ev_k + kSlots;
+  // everything queued so far on the chain stream (setters, earlier updates) precedes this update's first kernel by stream order
+  uint32_t k = 0;
+  for (uint32_t c0 = 0; c0 < chain->C; c0 += Cc, ++k) {
+    const uint32_t nc = std::min(Cc, chain->C - c0);
+    const int slot = (int)(k % kSlots);
+    int16_t *din = chain->d_in + (size_t)slot * slot_samples, *dout = chain->d_out + (size_t)slot * slot_samples;
+    if (k >= (uint32_t)kSlots) { // slot reuse: its previous kernel has read d_in, its previous D2H has drained d_out
+      CK(cudaStreamWaitEvent(chain->copy_in, ev_k[slot], 0));
+      CK(cudaStreamWaitEvent(chain->stream, ev_d2h[slot], 0));
+    }
+    CK(cudaMemcpy2DAsync(din, L * 2, in + (size_t)c0 * stride, stride * 2, L * 2, nc, cudaMemcpyHostToDevice, chain->copy_in));
+    CK(cudaEventRecord(ev_h2d[slot], chain->copy_in));
+    CK(cudaStreamWaitEvent(chain->stream, ev_h2d[slot], 0));
+    st = msdr_chain_update_range_device(chain, c0, nc, din, dout, n_blocks, L);
+    if (st != MSDR_OK) return st;
+    CK(cudaEventRecord(ev_k[slot], chain->stream));
+    CK(cudaStreamWaitEvent(chain->copy_out, ev_k[slot], 0));
+    CK(cudaMemcpy2DAsync(out + (size_t)c0 * stride, stride * 2, dout, L * 2, L * 2, nc, cudaMemcpyDeviceToHost, chain->copy_out));
+    CK(cudaEventRecord(ev_d2h[slot], chain->copy_out));
+  }
+  CK(cudaStreamSynchronize(chain->copy_out));
   CK(cudaStreamSynchronize(chain->stream));
   return MSDR_OK;
 }

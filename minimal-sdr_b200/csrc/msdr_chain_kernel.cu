@@ -245,7 +245,8 @@ __global__ void __launch_bounds__((NF + 2) * 32, 1) chain_kernel(const ChainPara
       const int tile_begin = seg * (int)p.TPS;
       const int tile_end = min(tile_begin + (int)p.TPS, (int)p.NT);
       const int nrows = min(kGroup, (int)p.C - grp * kGroup);
-      const uint32_t ch = (uint32_t)(grp * kGroup + lane);
+      const uint32_t row = (uint32_t)(grp * kGroup + lane); // row of in/out
+      const uint32_t ch = p.ch0 + row;                      // channel of the chain
       uint32_t rinfo = 0;
       if (lane < nrows) {
         const uint32_t set = p.setid[ch];
@@ -274,11 +275,11 @@ __global__ void __launch_bounds__((NF + 2) * 32, 1) chain_kernel(const ChainPara
         if (lane < nrows) {
           int16_t *dst = reinterpret_cast<int16_t *>(raw_base + (uint32_t)s * raw_stage) + (uint32_t)lane * RS;
           if ((uint32_t)t0 >= p.H) {
-            bulk_g2s(dst, p.in + (size_t)ch * p.stride + (size_t)(t0 - (int)p.H), row_bytes, &pc->full[s]);
+            bulk_g2s(dst, p.in + (size_t)row * p.stride + (size_t)(t0 - (int)p.H), row_bytes, &pc->full[s]);
           } else { // halo (partly) from the carried history
             const uint32_t nh = p.H - (uint32_t)t0;
             bulk_g2s(dst, p.hist + (size_t)ch * p.H + (size_t)t0, nh * 2u, &pc->full[s]);
-            bulk_g2s(dst + nh, p.in + (size_t)ch * p.stride, (uint32_t)(t0 + len) * 2u, &pc->full[s]);
+            bulk_g2s(dst + nh, p.in + (size_t)row * p.stride, (uint32_t)(t0 + len) * 2u, &pc->full[s]);
           }
         }
       }
@@ -313,13 +314,14 @@ __global__ void __launch_bounds__((NF + 2) * 32, 1) chain_kernel(const ChainPara
       // i.e. every odd word of the row
       {
         const int q4 = (int)((p.H + (uint32_t)td.len) >> 3); // uint4 per row
-        for (int idx = ftid; idx < nrows * q4; idx += NF * 32) {
-          const int r = idx / q4, c4 = idx - r * q4;
-          uint4 *pw = reinterpret_cast<uint4 *>(rawW + (uint32_t)r * (RS >> 1)) + c4;
-          uint4 v = *pw;
-          v.y = neg16x2(v.y);
-          v.w = neg16x2(v.w);
-          *pw = v;
+        for (int r = warp - 1; r < nrows; r += NF) {
+          uint4 *pw = reinterpret_cast<uint4 *>(rawW + (uint32_t)r * (RS >> 1));
+          for (int c4 = lane; c4 < q4; c4 += 32) {
+            uint4 v = pw[c4];
+            v.y = neg16x2(v.y);
+            v.w = neg16x2(v.w);
+            pw[c4] = v;
+          }
         }
       }
       named_bar_sync(1, NF * 32);
@@ -357,17 +359,18 @@ __global__ void __launch_bounds__((NF + 2) * 32, 1) chain_kernel(const ChainPara
       mbar_wait(&pc->dfull[s], ph);
       const TileDesc td = pc->ddesc[s];
       if (td.flags & TF_END) break;
-      const uint32_t ch = (uint32_t)(td.grp * kGroup + lane);
-      const bool active = ch < p.C;
+      const uint32_t row = (uint32_t)(td.grp * kGroup + lane);
+      const uint32_t ch = p.ch0 + row;
+      const bool active = row < p.C;
       uint32_t *drow = reinterpret_cast<uint32_t *>(d_base + (uint32_t)s * d_stage) + (uint32_t)lane * DW;
 
       if (td.flags & TF_SEG_FIRST) {
         if (td.seg > 0) { // state hand-off from the CTA that ran the previous segment of this group
           if (lane == 0) {
-            uint32_t spins = 0;
+            const long long t0 = clock64();
             while (ld_acquire_gpu(flags + td.grp) < td.seg) {
               __nanosleep(64);
-              if (++spins > (1u << 24)) __trap();
+              if (clock64() - t0 > kWatchdogCycles) __trap();
             }
           }
           __syncwarp();
@@ -429,7 +432,7 @@ __global__ void __launch_bounds__((NF + 2) * 32, 1) chain_kernel(const ChainPara
 
       // drain the finished tile to HBM: one bulk copy per channel row
       fence_proxy_async_smem();
-      if (active) bulk_s2g(p.out + (size_t)ch * p.stride + (size_t)td.t0, drow, (uint32_t)td.len * 2u);
+      if (active) bulk_s2g(p.out + (size_t)row * p.stride + (size_t)td.t0, drow, (uint32_t)td.len * 2u);
       bulk_commit();
       if (it > 0) { // the previous tile's buffer is free once its copy has finished reading shared memory
         bulk_wait_read<1>();
@@ -448,7 +451,7 @@ __global__ void __launch_bounds__((NF + 2) * 32, 1) chain_kernel(const ChainPara
           const uint32_t hq = p.H >> 3; // uint4 per history row (<= 33)
           for (int r = 0; r < nrows; ++r) {
             const size_t c = (size_t)(td.grp * kGroup + r);
-            uint4 *hrow = reinterpret_cast<uint4 *>(p.hist + c * p.H);
+            uint4 *hrow = reinterpret_cast<uint4 *>(p.hist + ((size_t)p.ch0 + c) * p.H);
             const uint4 *irow = reinterpret_cast<const uint4 *>(p.in + c * p.stride);
             uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
             const uint32_t i0 = (uint32_t)lane, i1 = (uint32_t)lane + 32u;

@@ -18,7 +18,8 @@ struct ChainParams {
   const int16_t *in;      // [C][stride]
   int16_t *out;           // [C][stride]
   size_t stride;          // samples
-  uint32_t C;             // channels
+  uint32_t C;             // channels processed by this launch: chain channels [ch0, ch0 + C)
+  uint32_t ch0;           // first chain channel (indexes hist/bq/mode/setid); in/out rows are launch-relative
   uint32_t Cpad;          // row pitch of the SoA state arrays (multiple of 32)
   uint32_t L;             // samples per channel in this launch (multiple of 128)
   uint32_t H;             // history / halo length in samples (multiple of 8)
