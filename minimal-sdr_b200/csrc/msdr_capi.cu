@@ -71,7 +71,7 @@ struct msdr_chain {
   size_t pin_samples = 0;
 
   int variant = 0;
-  uint32_t host_chunk_channels = 0; // 0 = auto
+  uint32_t host_chunk_channels = 0, host_chunk_blocks = 0; // 0 = auto
   uint64_t launches = 0;
   std::string err;
   ChainLaunchInfo last_info{};
@@ -372,13 +372,16 @@ int msdr_chain_update(msdr_chain *chain, const int16_t *in, int16_t *out, uint32
   if (chain->n_uninit) return fail(chain, MSDR_ERR_NOT_INITIALISED, "update: some channels have no FIR bound (call msdr_fir_init_q15)");
   CK(cudaSetDevice(chain->device));
   constexpr int kSlots = 3;
+  // chunk = (channel range) x (block range).  Whole channel set and ~64 MiB per direction when it fits, so each kernel
+  // still sees thousands of channels; huge chains are cut along channels as well.
   uint32_t Cc = chain->host_chunk_channels;
-  if (Cc == 0) { // ~32 MiB per chunk and direction
-    Cc = (uint32_t)std::max<size_t>(kGroup, ((size_t)32 << 20) / (L * 2) / kGroup * kGroup);
-  }
-  Cc = std::min(Cc, (chain->C + kGroup - 1) / kGroup * kGroup);
-  Cc = std::max<uint32_t>(kGroup, Cc / kGroup * kGroup);
-  const size_t slot_samples = (size_t)Cc * L;
+  if (Cc == 0) Cc = 1u << 19;
+  Cc = std::max<uint32_t>(kGroup, std::min(Cc, (chain->C + kGroup - 1) / kGroup * kGroup) / kGroup * kGroup);
+  uint32_t nbk = chain->host_chunk_blocks;
+  if (nbk == 0) nbk = (uint32_t)std::max<size_t>(1, ((size_t)64 << 20) / ((size_t)std::min(Cc, chain->C) * MSDR_BLOCK_SAMPLES * 2));
+  nbk = std::min(nbk, n_blocks);
+  const size_t Lc = (size_t)nbk * MSDR_BLOCK_SAMPLES; // device row pitch of a chunk
+  const size_t slot_samples = (size_t)Cc * Lc;
   int st = ensure_stage(chain, slot_samples * kSlots);
   if (st != MSDR_OK) return st;
   if (chain->pipe_ev.empty()) {
@@ -388,23 +391,28 @@ int msdr_chain_update(msdr_chain *chain, const int16_t *in, int16_t *out, uint32
   cudaEvent_t *ev_h2d = chain->pipe_ev.data(), *ev_k = ev_h2d + kSlots, *ev_d2h = ev_k + kSlots;
   // everything queued so far on the chain stream (setters, earlier updates) precedes this update's first kernel by stream order
   uint32_t k = 0;
-  for (uint32_t c0 = 0; c0 < chain->C; c0 += Cc, ++k) {
+  for (uint32_t c0 = 0; c0 < chain->C; c0 += Cc) {
     const uint32_t nc = std::min(Cc, chain->C - c0);
-    const int slot = (int)(k % kSlots);
-    int16_t *din = chain->d_in + (size_t)slot * slot_samples, *dout = chain->d_out + (size_t)slot * slot_samples;
-    if (k >= (uint32_t)kSlots) { // slot reuse: its previous kernel has read d_in, its previous D2H has drained d_out
-      CK(cudaStreamWaitEvent(chain->copy_in, ev_k[slot], 0));
-      CK(cudaStreamWaitEvent(chain->stream, ev_d2h[slot], 0));
+    for (uint32_t b0 = 0; b0 < n_blocks; b0 += nbk, ++k) { // time order within a channel range: state carries
+      const uint32_t nb = std::min(nbk, n_blocks - b0);
+      const size_t w = (size_t)nb * MSDR_BLOCK_SAMPLES * 2; // bytes per row in this chunk
+      const int slot = (int)(k % kSlots);
+      int16_t *din = chain->d_in + (size_t)slot * slot_samples, *dout = chain->d_out + (size_t)slot * slot_samples;
+      const size_t hoff = (size_t)c0 * stride + (size_t)b0 * MSDR_BLOCK_SAMPLES;
+      if (k >= (uint32_t)kSlots) { // slot reuse: its previous kernel has read d_in, its previous D2H has drained d_out
+        CK(cudaStreamWaitEvent(chain->copy_in, ev_k[slot], 0));
+        CK(cudaStreamWaitEvent(chain->stream, ev_d2h[slot], 0));
+      }
+      CK(cudaMemcpy2DAsync(din, Lc * 2, in + hoff, stride * 2, w, nc, cudaMemcpyHostToDevice, chain->copy_in));
+      CK(cudaEventRecord(ev_h2d[slot], chain->copy_in));
+      CK(cudaStreamWaitEvent(chain->stream, ev_h2d[slot], 0));
+      st = msdr_chain_update_range_device(chain, c0, nc, din, dout, nb, Lc);
+      if (st != MSDR_OK) return st;
+      CK(cudaEventRecord(ev_k[slot], chain->stream));
+      CK(cudaStreamWaitEvent(chain->copy_out, ev_k[slot], 0));
+      CK(cudaMemcpy2DAsync(out + hoff, stride * 2, dout, Lc * 2, w, nc, cudaMemcpyDeviceToHost, chain->copy_out));
+      CK(cudaEventRecord(ev_d2h[slot], chain->copy_out));
     }
-    CK(cudaMemcpy2DAsync(din, L * 2, in + (size_t)c0 * stride, stride * 2, L * 2, nc, cudaMemcpyHostToDevice, chain->copy_in));
-    CK(cudaEventRecord(ev_h2d[slot], chain->copy_in));
-    CK(cudaStreamWaitEvent(chain->stream, ev_h2d[slot], 0));
-    st = msdr_chain_update_range_device(chain, c0, nc, din, dout, n_blocks, L);
-    if (st != MSDR_OK) return st;
-    CK(cudaEventRecord(ev_k[slot], chain->stream));
-    CK(cudaStreamWaitEvent(chain->copy_out, ev_k[slot], 0));
-    CK(cudaMemcpy2DAsync(out + (size_t)c0 * stride, stride * 2, dout, L * 2, L * 2, nc, cudaMemcpyDeviceToHost, chain->copy_out));
-    CK(cudaEventRecord(ev_d2h[slot], chain->copy_out));
   }
   CK(cudaStreamSynchronize(chain->copy_out));
   CK(cudaStreamSynchronize(chain->stream));
@@ -427,6 +435,7 @@ int msdr_chain_set_option(msdr_chain *chain, const char *key, int value)
   if (!strcmp(key, "variant")) { chain->variant = value; return MSDR_OK; }
   if (!strcmp(key, "timing")) { chain->timed = value != 0; return MSDR_OK; }
   if (!strcmp(key, "host_chunk_channels")) { chain->host_chunk_channels = (uint32_t)value; return MSDR_OK; }
+  if (!strcmp(key, "host_chunk_blocks")) { chain->host_chunk_blocks = (uint32_t)value; return MSDR_OK; }
   return fail(chain, MSDR_ERR_ARGUMENT, std::string("unknown option ") + key);
 }
 

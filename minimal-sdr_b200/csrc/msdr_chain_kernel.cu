@@ -168,7 +168,7 @@ __device__ __forceinline__ int demod_kind_of(int mode, uint32_t am_q31)
   return am_q31 ? 3 : 2;
 }
 
-// two samples (one packed word) through NS fused stages; values carried as v << 16
+// two samples (one packed word) through NS fused stages — integer (IMAD.HI) representation, values carried as v << 16
 template <int NS>
 __device__ __forceinline__ uint32_t bq_word(BqStage (&st)[NS], uint32_t w)
 {
@@ -178,6 +178,18 @@ __device__ __forceinline__ uint32_t bq_word(BqStage (&st)[NS], uint32_t w)
 #pragma unroll
   for (int k = 0; k < NS; ++k) xo = bq_step(st[k], xo);
   return __byte_perm((uint32_t)xe, (uint32_t)xo, 0x7632);
+}
+// same on the FP64 pipe (D-form values)
+template <int NS>
+__device__ __forceinline__ uint32_t bq_word(BqStageD (&st)[NS], uint32_t w)
+{
+  double xe = bq_d_from_int((int)(short)(w & 0xFFFFu)), xo = bq_d_from_int((int)w >> 16);
+  int ye = 0, yo = 0;
+#pragma unroll
+  for (int k = 0; k < NS; ++k) xe = bq_step(st[k], xe, ye);
+#pragma unroll
+  for (int k = 0; k < NS; ++k) xo = bq_step(st[k], xo, yo);
+  return __byte_perm((uint32_t)ye, (uint32_t)yo, 0x5410);
 }
 
 __device__ __forceinline__ void bq_load_stage(BqStage &s, uint32_t &flag, const int32_t *__restrict__ bq, uint32_t Cpad, int obj, int stage, uint32_t ch)
@@ -201,8 +213,27 @@ __device__ __forceinline__ void bq_store_stage(const BqStage &s, uint32_t flag, 
   b[6 * (size_t)Cpad] = (int32_t)bq_pack_hist(s.y1, s.y2);
   b[7 * (size_t)Cpad] = (int32_t)((uint32_t)s.res | flag); // filter_biquad.cpp:75-78
 }
+__device__ __forceinline__ void bq_load_stage(BqStageD &s, uint32_t &flag, const int32_t *__restrict__ bq, uint32_t Cpad, int obj, int stage, uint32_t ch)
+{
+  const int32_t *b = bq + (size_t)((obj * 4 + stage) * 8) * Cpad + ch;
+  bq_set_coefs(s, __ldcg(b + 0 * (size_t)Cpad), __ldcg(b + 1 * (size_t)Cpad), __ldcg(b + 2 * (size_t)Cpad), __ldcg(b + 3 * (size_t)Cpad),
+               __ldcg(b + 4 * (size_t)Cpad));
+  const uint32_t w5 = (uint32_t)__ldcg(b + 5 * (size_t)Cpad), w6 = (uint32_t)__ldcg(b + 6 * (size_t)Cpad);
+  s.x1 = bq_d_from_int((int)w5 >> 16); s.x2 = bq_d_from_int((int)(short)(w5 & 0xFFFFu));
+  s.y1 = bq_d_from_int((int)w6 >> 16); s.y2 = bq_d_from_int((int)(short)(w6 & 0xFFFFu));
+  const uint32_t w7 = (uint32_t)__ldcg(b + 7 * (size_t)Cpad);
+  s.res = (int)(w7 & 0x3FFFu);
+  flag = w7 & 0x80000000u;
+}
+__device__ __forceinline__ void bq_store_stage(const BqStageD &s, uint32_t flag, int32_t *__restrict__ bq, uint32_t Cpad, int obj, int stage, uint32_t ch)
+{
+  int32_t *b = bq + (size_t)((obj * 4 + stage) * 8) * Cpad + ch;
+  b[5 * (size_t)Cpad] = (int32_t)(((uint32_t)bq_int_from_d(s.x1) << 16) | ((uint32_t)bq_int_from_d(s.x2) & 0xFFFFu));
+  b[6 * (size_t)Cpad] = (int32_t)(((uint32_t)bq_int_from_d(s.y1) << 16) | ((uint32_t)bq_int_from_d(s.y2) & 0xFFFFu));
+  b[7 * (size_t)Cpad] = (int32_t)((uint32_t)s.res | flag);
+}
 
-template <int TT, int NF>
+template <int TT, int NF, class BQ>
 __global__ void __launch_bounds__((NF + 2) * 32, 1) chain_kernel(const ChainParams p)
 {
   constexpr int R = TT / 64;      // output pairs per lane
@@ -349,7 +380,7 @@ __global__ void __launch_bounds__((NF + 2) * 32, 1) chain_kernel(const ChainPara
   } else {
     // ------------------------------------------------------------------ biquad warp (lane = channel)
     int *flags = p.ctrl + 1;
-    BqStage st[2];
+    BQ st[2];
     uint32_t fl[2] = {0u, 0u};
     int nst0 = 1, nst1 = 1;
     bool fast = true;
@@ -411,7 +442,7 @@ __global__ void __launch_bounds__((NF + 2) * 32, 1) chain_kernel(const ChainPara
             const bool has = active && k < myn;
             if (!__any_sync(0xffffffffu, has)) break;
             if (has) {
-              BqStage g[1];
+              BQ g[1];
               uint32_t gf;
               bq_load_stage(g[0], gf, p.bq, p.Cpad, obj, k, ch);
               uint4 *dp = reinterpret_cast<uint4 *>(drow);
@@ -434,11 +465,10 @@ __global__ void __launch_bounds__((NF + 2) * 32, 1) chain_kernel(const ChainPara
       fence_proxy_async_smem();
       if (active) bulk_s2g(p.out + (size_t)row * p.stride + (size_t)td.t0, drow, (uint32_t)td.len * 2u);
       bulk_commit();
-      if (it > 0) { // the previous tile's buffer is free once its copy has finished reading shared memory
-        bulk_wait_read<1>();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&pc->dfree[s ^ 1]);
-      }
+      // the buffer is reusable as soon as the copy engine has READ it (not when the data has landed in HBM)
+      bulk_wait_read<0>();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&pc->dfree[s]);
 
       if (td.flags & TF_SEG_LAST) {
         if (fast && active) {
@@ -480,7 +510,6 @@ __global__ void __launch_bounds__((NF + 2) * 32, 1) chain_kernel(const ChainPara
 
 cudaError_t launch_chain(const ChainParams &p_in, cudaStream_t stream, int variant, ChainLaunchInfo *info)
 {
-  (void)variant;
   constexpr int TT = 512, NF = 8;
   ChainParams p = p_in;
   int dev = 0, sms = 0;
@@ -500,7 +529,8 @@ cudaError_t launch_chain(const ChainParams &p_in, cudaStream_t stream, int varia
   p.n_items = p.NG * p.S;
 
   const size_t smem = chain_smem_bytes(p.H, p.n_sets, p.set_stride_words, TT);
-  auto kern = chain_kernel<TT, NF>;
+  // variant bit 0: biquad products on IMAD.HI (integer pipe) instead of DFMA (FP64 pipe)
+  auto kern = (variant & 1) ? chain_kernel<TT, NF, BqStage> : chain_kernel<TT, NF, BqStageD>;
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int per_sm = 0;

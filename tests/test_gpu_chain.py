@@ -272,6 +272,7 @@ def test_host_update_pipeline_chunks(msdr, orc, K):
     x = msdr.synth.batch(modes, 128 * 9)
     g, o = configure_pair(msdr, orc, K, modes)
     g.set_option("host_chunk_channels", 32)
+    g.set_option("host_chunk_blocks", 2)
     yg, yo = run_pair(g, o, x, splits=[2, 7])
     assert_same(yg, yo, "chunked host update")
     pin, pout = msdr.capi.PinnedBuffer(x.shape), msdr.capi.PinnedBuffer(x.shape)
