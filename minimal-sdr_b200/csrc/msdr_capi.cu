@@ -63,6 +63,9 @@ struct msdr_chain {
   int32_t *d_sets = nullptr;
   uint32_t *d_set_kp4 = nullptr;
   int *d_ctrl = nullptr;
+  int *d_tile_flags = nullptr; // [groups][tiles] of the largest launch so far
+  size_t tile_flags_len = 0;
+  uint32_t epoch = 0;
 
   // staging for host-buffer updates
   int16_t *d_in = nullptr, *d_out = nullptr;
@@ -230,7 +233,7 @@ void msdr_chain_destroy(msdr_chain *chain)
   cudaSetDevice(chain->device);
   if (chain->stream) cudaStreamSynchronize(chain->stream);
   cudaFree(chain->d_mode); cudaFree(chain->d_set); cudaFree(chain->d_hist); cudaFree(chain->d_bq);
-  cudaFree(chain->d_sets); cudaFree(chain->d_set_kp4); cudaFree(chain->d_ctrl);
+  cudaFree(chain->d_sets); cudaFree(chain->d_set_kp4); cudaFree(chain->d_ctrl); cudaFree(chain->d_tile_flags);
   cudaFree(chain->d_in); cudaFree(chain->d_out);
   if (chain->pin_in) cudaFreeHost(chain->pin_in);
   if (chain->pin_out) cudaFreeHost(chain->pin_out);
@@ -347,6 +350,20 @@ int msdr_chain_update_range_device(msdr_chain *chain, uint32_t ch0, uint32_t nch
   p.ctrl = chain->d_ctrl;
   p.am_q31 = (chain->flags & MSDR_FLAG_AM_Q31) ? 1u : 0u;
   const uint32_t NG = (nch + kGroup - 1) / kGroup;
+  const size_t n_flags = (size_t)NG * ((p.L + chain_tile_samples() - 1) / chain_tile_samples());
+  if (n_flags > chain->tile_flags_len || chain->epoch >= 0x7FFFFFF0u) { // (re)allocate zeroed flags; epochs restart
+    CK(cudaStreamSynchronize(chain->stream));
+    if (chain->d_tile_flags) cudaFree(chain->d_tile_flags);
+    chain->d_tile_flags = nullptr;
+    chain->tile_flags_len = 0;
+    const size_t len = std::max(n_flags, chain->tile_flags_len) + 1024;
+    CK(cudaMalloc(&chain->d_tile_flags, len * sizeof(int)));
+    CK(cudaMemsetAsync(chain->d_tile_flags, 0, len * sizeof(int), chain->stream));
+    chain->tile_flags_len = len;
+    chain->epoch = 0;
+  }
+  p.tile_flags = chain->d_tile_flags;
+  p.epoch = ++chain->epoch;
   CK(cudaMemsetAsync(chain->d_ctrl, 0, (size_t)(1 + NG) * sizeof(int), chain->stream));
   if (chain->timed) CK(cudaEventRecord(chain->ev0, chain->stream));
   CK(launch_chain(p, chain->stream, chain->variant, &chain->last_info));

@@ -22,8 +22,7 @@
 // The only serial dependence across time is the biquad state.  Work items are ordered segment-major and the
 // biquad warp hands its state to the CTA that owns the next segment of the same channel group through global
 // memory + a release/acquire flag, so FIR work balances over all SMs for any channel count.
-#include "msdr_device.cuh"
-#include "msdr_internal.h"
+#include "msdr_chain_common.cuh"
 
 namespace msdr {
 
@@ -51,186 +50,12 @@ struct __align__(16) PipeCtrl {
 static_assert(sizeof(PipeCtrl) <= 512, "PipeCtrl must fit its smem slot");
 constexpr uint32_t kCtrlBytes = 512;
 
-__host__ __device__ inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1u) / a * a; }
-
 size_t chain_smem_bytes(uint32_t H, uint32_t n_sets, uint32_t set_stride_words, int tile)
 {
   const uint32_t sets_bytes = align_up(n_sets * set_stride_words * 4u, 128u);
   const uint32_t raw_stage = kGroup * (H + (uint32_t)tile) * 2u;
   const uint32_t d_stage = kGroup * ((uint32_t)tile / 2u + 4u) * 4u;
   return (size_t)kCtrlBytes + sets_bytes + 2u * raw_stage + 2u * d_stage;
-}
-
-__device__ __forceinline__ void unpack4(const uint4 v, uint32_t *e, uint32_t *o)
-{
-  e[0] = (uint32_t)(int)(short)(v.x & 0xFFFFu); o[0] = (uint32_t)((int)v.x >> 16);
-  e[1] = (uint32_t)(int)(short)(v.y & 0xFFFFu); o[1] = (uint32_t)((int)v.y >> 16);
-  e[2] = (uint32_t)(int)(short)(v.z & 0xFFFFu); o[2] = (uint32_t)((int)v.z >> 16);
-  e[3] = (uint32_t)(int)(short)(v.w & 0xFFFFu); o[3] = (uint32_t)((int)v.w >> 16);
-}
-
-// One channel row of one tile: FIR pair + demod for lane's 2R output samples.
-//   rowW  : sign-folded raw samples of the row as words (even sample | odd sample << 16); word Hw is tile sample 0
-//   cf    : expanded taps of the row's coefficient set: per 4-tap chunk c, cf[4c+0..3] = A, B, C, D sub-filters
-//           A: I taps for odd outputs, B: I taps for even outputs, C: Q taps for odd outputs, D: Q taps for even
-//   With u = folded samples, ue[j] = u[2j], uo[j] = u[2j+1], output pair i = (n = 2i, 2i+1), KP = 4*kp4:
-//     accX[i] = sum_{d < KP} cX[d] * {ue|uo}[i - KP + 1 + d]      (exact mod 2^32, any order)
-// 4 taps x R output pairs x 4 sub-filters = 16R multiply-accumulates on a rotating register window.
-// The window holds W = R + 4 consecutive words; logical position x lives in physical register (x + 4*ROT) % W, so
-// sliding the window by one chunk (4 words) is a change of ROT, not a register move.
-template <int R, int ROT>
-__device__ __forceinline__ void fir_chunk(uint32_t (&e)[R + 4], uint32_t (&o)[R + 4], uint32_t (&aA)[R], uint32_t (&aB)[R], uint32_t (&aC)[R],
-                                          uint32_t (&aD)[R], const int4 *__restrict__ cf)
-{
-  constexpr int W = R + 4;
-  const int4 cA = cf[0], cB = cf[1], cC = cf[2], cD = cf[3];
-  const uint32_t ca[4] = {(uint32_t)cA.x, (uint32_t)cA.y, (uint32_t)cA.z, (uint32_t)cA.w};
-  const uint32_t cb[4] = {(uint32_t)cB.x, (uint32_t)cB.y, (uint32_t)cB.z, (uint32_t)cB.w};
-  const uint32_t cc[4] = {(uint32_t)cC.x, (uint32_t)cC.y, (uint32_t)cC.z, (uint32_t)cC.w};
-  const uint32_t cd[4] = {(uint32_t)cD.x, (uint32_t)cD.y, (uint32_t)cD.z, (uint32_t)cD.w};
-#pragma unroll
-  for (int t = 0; t < 4; ++t) {
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const uint32_t ev = e[(1 + r + t + 4 * ROT) % W], ov = o[(1 + r + t + 4 * ROT) % W];
-      aA[r] = ca[t] * ev + aA[r];
-      aB[r] = cb[t] * ev + aB[r];
-      aC[r] = cc[t] * ov + aC[r];
-      aD[r] = cd[t] * ov + aD[r];
-    }
-  }
-}
-
-// One channel row of one tile: FIR pair + demod for lane's 2R output samples.
-//   rowW  : sign-folded raw samples of the row as words (even sample | odd sample << 16); word Hw is tile sample 0
-//   cf    : expanded taps of the row's coefficient set: per 4-tap chunk c, cf[4c+0..3] = A, B, C, D sub-filters
-//           A: I taps for odd outputs, B: I taps for even outputs, C: Q taps for odd outputs, D: Q taps for even
-//   With u = folded samples, ue[j] = u[2j], uo[j] = u[2j+1], output pair i = (n = 2i, 2i+1), KP = 4*kp4:
-//     accX[i] = sum_{d < KP} cX[d] * {ue|uo}[i - KP + 1 + d]      (exact mod 2^32, any order)
-template <int R>
-__device__ __forceinline__ void fir_demod_row(const uint32_t *__restrict__ rowW, const int4 *__restrict__ cf, const int kp4, const int Hw,
-                                              const int lane, const int len, const int kind, uint32_t *__restrict__ drow)
-{
-  static_assert(R == 8, "the rotation schedule below assumes a 12-word window (3 chunks per turn)");
-  constexpr int W = R + 4;
-  const int i0 = lane * R;
-  if (2 * i0 >= len) return;
-  const uint4 *wp = reinterpret_cast<const uint4 *>(rowW + Hw + i0 - 4 * kp4);
-  uint32_t e[W], o[W];
-#pragma unroll
-  for (int g = 0; g < W / 4; ++g) unpack4(wp[g], e + 4 * g, o + 4 * g);
-  wp += W / 4;
-  uint32_t aA[R], aB[R], aC[R], aD[R];
-#pragma unroll
-  for (int r = 0; r < R; ++r) aA[r] = aB[r] = aC[r] = aD[r] = 0u;
-
-  // chunk c consumes window rotation c % 3 and then refills the 4 slots it vacated with words for chunk c + 1;
-  // the refill after the very last chunk reads 4 words past the lane's window (still inside the row buffer) and is unused.
-  int c = 0;
-#pragma unroll 1
-  for (; c + 3 <= kp4; c += 3) {
-    fir_chunk<R, 0>(e, o, aA, aB, aC, aD, cf + 4 * c);
-    unpack4(wp[0], e + 0, o + 0);
-    fir_chunk<R, 1>(e, o, aA, aB, aC, aD, cf + 4 * c + 4);
-    unpack4(wp[1], e + 4, o + 4);
-    fir_chunk<R, 2>(e, o, aA, aB, aC, aD, cf + 4 * c + 8);
-    unpack4(wp[2], e + 8, o + 8);
-    wp += 3;
-  }
-  if (c < kp4) {
-    fir_chunk<R, 0>(e, o, aA, aB, aC, aD, cf + 4 * c);
-    if (c + 1 < kp4) {
-      unpack4(wp[0], e + 0, o + 0);
-      fir_chunk<R, 1>(e, o, aA, aB, aC, aD, cf + 4 * c + 4);
-    }
-  }
-
-  // arm_fir_fast_q15.c:234-238: acc >> 15, SSAT16; then the demodulation switch (Minimal-SDR.ino:589-628)
-  uint32_t outw[R];
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const int Io = ssat16((int)aA[r] >> 15), Ie = ssat16((int)aB[r] >> 15);
-    const int Qo = ssat16((int)aC[r] >> 15), Qe = ssat16((int)aD[r] >> 15);
-    const int se = demod_sample(kind, Ie, Qe), so = demod_sample(kind, Io, Qo);
-    outw[r] = ((uint32_t)se & 0xFFFFu) | ((uint32_t)so << 16);
-  }
-  uint4 *dp = reinterpret_cast<uint4 *>(drow + i0);
-#pragma unroll
-  for (int g = 0; g < R / 4; ++g) dp[g] = make_uint4(outw[4 * g], outw[4 * g + 1], outw[4 * g + 2], outw[4 * g + 3]);
-}
-
-__device__ __forceinline__ int demod_kind_of(int mode, uint32_t am_q31)
-{
-  // Minimal-SDR.ino:589-628: LSB, USB; AM/CW (+SYNCAM on Teensy 3.2) envelope
-  if (mode == 2) return 0;
-  if (mode == 3) return 1;
-  if (mode == 0) return 3;
-  return am_q31 ? 3 : 2;
-}
-
-// two samples (one packed word) through NS fused stages — integer (IMAD.HI) representation, values carried as v << 16
-template <int NS>
-__device__ __forceinline__ uint32_t bq_word(BqStage (&st)[NS], uint32_t w)
-{
-  int xe = (int)(w << 16), xo = (int)(w & 0xFFFF0000u);
-#pragma unroll
-  for (int k = 0; k < NS; ++k) xe = bq_step(st[k], xe);
-#pragma unroll
-  for (int k = 0; k < NS; ++k) xo = bq_step(st[k], xo);
-  return __byte_perm((uint32_t)xe, (uint32_t)xo, 0x7632);
-}
-// same on the FP64 pipe (D-form values)
-template <int NS>
-__device__ __forceinline__ uint32_t bq_word(BqStageD (&st)[NS], uint32_t w)
-{
-  double xe = bq_d_from_int((int)(short)(w & 0xFFFFu)), xo = bq_d_from_int((int)w >> 16);
-  int ye = 0, yo = 0;
-#pragma unroll
-  for (int k = 0; k < NS; ++k) xe = bq_step(st[k], xe, ye);
-#pragma unroll
-  for (int k = 0; k < NS; ++k) xo = bq_step(st[k], xo, yo);
-  return __byte_perm((uint32_t)ye, (uint32_t)yo, 0x5410);
-}
-
-__device__ __forceinline__ void bq_load_stage(BqStage &s, uint32_t &flag, const int32_t *__restrict__ bq, uint32_t Cpad, int obj, int stage, uint32_t ch)
-{
-  const int32_t *b = bq + (size_t)((obj * 4 + stage) * 8) * Cpad + ch;
-  s.b0 = __ldcg(b + 0 * (size_t)Cpad);
-  s.b1 = __ldcg(b + 1 * (size_t)Cpad);
-  s.b2 = __ldcg(b + 2 * (size_t)Cpad);
-  s.a1 = __ldcg(b + 3 * (size_t)Cpad);
-  s.a2 = __ldcg(b + 4 * (size_t)Cpad);
-  bq_unpack_hist((uint32_t)__ldcg(b + 5 * (size_t)Cpad), s.x1, s.x2);
-  bq_unpack_hist((uint32_t)__ldcg(b + 6 * (size_t)Cpad), s.y1, s.y2);
-  const uint32_t w7 = (uint32_t)__ldcg(b + 7 * (size_t)Cpad);
-  s.res = (int)(w7 & 0x3FFFu); // filter_biquad.cpp:52
-  flag = w7 & 0x80000000u;
-}
-__device__ __forceinline__ void bq_store_stage(const BqStage &s, uint32_t flag, int32_t *__restrict__ bq, uint32_t Cpad, int obj, int stage, uint32_t ch)
-{
-  int32_t *b = bq + (size_t)((obj * 4 + stage) * 8) * Cpad + ch;
-  b[5 * (size_t)Cpad] = (int32_t)bq_pack_hist(s.x1, s.x2);
-  b[6 * (size_t)Cpad] = (int32_t)bq_pack_hist(s.y1, s.y2);
-  b[7 * (size_t)Cpad] = (int32_t)((uint32_t)s.res | flag); // filter_biquad.cpp:75-78
-}
-__device__ __forceinline__ void bq_load_stage(BqStageD &s, uint32_t &flag, const int32_t *__restrict__ bq, uint32_t Cpad, int obj, int stage, uint32_t ch)
-{
-  const int32_t *b = bq + (size_t)((obj * 4 + stage) * 8) * Cpad + ch;
-  bq_set_coefs(s, __ldcg(b + 0 * (size_t)Cpad), __ldcg(b + 1 * (size_t)Cpad), __ldcg(b + 2 * (size_t)Cpad), __ldcg(b + 3 * (size_t)Cpad),
-               __ldcg(b + 4 * (size_t)Cpad));
-  const uint32_t w5 = (uint32_t)__ldcg(b + 5 * (size_t)Cpad), w6 = (uint32_t)__ldcg(b + 6 * (size_t)Cpad);
-  s.x1 = bq_d_from_int((int)w5 >> 16); s.x2 = bq_d_from_int((int)(short)(w5 & 0xFFFFu));
-  s.y1 = bq_d_from_int((int)w6 >> 16); s.y2 = bq_d_from_int((int)(short)(w6 & 0xFFFFu));
-  const uint32_t w7 = (uint32_t)__ldcg(b + 7 * (size_t)Cpad);
-  s.res = (int)(w7 & 0x3FFFu);
-  flag = w7 & 0x80000000u;
-}
-__device__ __forceinline__ void bq_store_stage(const BqStageD &s, uint32_t flag, int32_t *__restrict__ bq, uint32_t Cpad, int obj, int stage, uint32_t ch)
-{
-  int32_t *b = bq + (size_t)((obj * 4 + stage) * 8) * Cpad + ch;
-  b[5 * (size_t)Cpad] = (int32_t)(((uint32_t)bq_int_from_d(s.x1) << 16) | ((uint32_t)bq_int_from_d(s.x2) & 0xFFFFu));
-  b[6 * (size_t)Cpad] = (int32_t)(((uint32_t)bq_int_from_d(s.y1) << 16) | ((uint32_t)bq_int_from_d(s.y2) & 0xFFFFu));
-  b[7 * (size_t)Cpad] = (int32_t)((uint32_t)s.res | flag);
 }
 
 template <int TT, int NF, class BQ>
@@ -508,7 +333,7 @@ __global__ void __launch_bounds__((NF + 2) * 32, 1) chain_kernel(const ChainPara
   }
 }
 
-cudaError_t launch_chain(const ChainParams &p_in, cudaStream_t stream, int variant, ChainLaunchInfo *info)
+cudaError_t launch_chain_handoff(const ChainParams &p_in, cudaStream_t stream, int variant, ChainLaunchInfo *info)
 {
   constexpr int TT = 512, NF = 8;
   ChainParams p = p_in;
@@ -530,7 +355,7 @@ cudaError_t launch_chain(const ChainParams &p_in, cudaStream_t stream, int varia
 
   const size_t smem = chain_smem_bytes(p.H, p.n_sets, p.set_stride_words, TT);
   // variant bit 0: biquad products on IMAD.HI (integer pipe) instead of DFMA (FP64 pipe)
-  auto kern = (variant & 1) ? chain_kernel<TT, NF, BqStage> : chain_kernel<TT, NF, BqStageD>;
+  auto kern = (variant & 1) ? chain_kernel<TT, NF, BqStageD> : chain_kernel<TT, NF, BqStage>;
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int per_sm = 0;

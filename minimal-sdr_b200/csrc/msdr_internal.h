@@ -36,7 +36,10 @@ struct ChainParams {
   uint32_t TPS;           // tiles per segment
   uint32_t S;             // segments per group
   uint32_t n_items;       // NG * S
-  int *ctrl;              // [0] work counter, [1 + g] segments completed for group g
+  int *ctrl;              // [0] work counter, [1 + g] segments completed for group g (hand-off kernel)
+  int *tile_flags;        // [NG][NT] == epoch once the demodulated tile is in `out` (chain kernel v3)
+  uint32_t epoch;         // launch counter, never 0
+  uint32_t W;             // biquad chains per wave = grid * chains per CTA (v3)
   uint32_t am_q31;
 };
 
@@ -48,6 +51,9 @@ struct ChainLaunchInfo {
 
 // Fused mix + FIR pair + demod + biquad cascade (K1). variant: 0 = default.
 cudaError_t launch_chain(const ChainParams &p, cudaStream_t stream, int variant, ChainLaunchInfo *info);
+cudaError_t launch_chain_handoff(const ChainParams &p, cudaStream_t stream, int variant, ChainLaunchInfo *info);
+cudaError_t launch_chain_v3(const ChainParams &p, cudaStream_t stream, int variant, ChainLaunchInfo *info);
+uint32_t chain_tile_samples();
 size_t chain_smem_bytes(uint32_t H, uint32_t n_sets, uint32_t set_stride_words, int tile);
 
 // stage-level kernels on device buffers
