@@ -218,7 +218,8 @@ def main():
     nb_total = (n_samples + BLOCK - 1) // BLOCK
     L = nb_total * BLOCK
     bpu = max(1, min(args.blocks_per_update, nb_total))
-    ch0 = rank * C  # this rank's shard of the global channel space
+    shard = m.shard.weak_scaling_shard(C, world, rank)  # this rank's slice of the global channel space
+    ch0 = shard.ch0
 
     g = m.ReceiveChain(C, device=local_rank)
     g.set_option("variant", args.variant)
@@ -260,10 +261,7 @@ def main():
     ms = e0.elapsed_time(e1)
     launches = g.launch_count() - l0
     clk = clocks.stop()
-    if world > 1:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = m.shard.max_over_ranks(ms, dev)  # multi-GPU timing rule: slowest rank
 
     samples_per_step = C * L
     value = world * samples_per_step * args.steps / (ms * 1e-3) / 1e6  # Msamples/s, whole job
@@ -281,10 +279,7 @@ def main():
             g.update(hin.array, out=hout.array)
         barrier()
         dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+        dt = m.shard.max_over_ranks(dt, dev)
         e2e = {"value": world * samples_per_step * args.e2e_steps / dt / 1e6, "unit": "Msamples/s",
                "h2d_bytes_per_step": int(samples_per_step * 2), "d2h_bytes_per_step": int(samples_per_step * 2), "steps": args.e2e_steps,
                "api": "msdr_chain_update (C ABI, pinned host buffers, whole batch per call)"}

@@ -56,5 +56,6 @@ def test_product_does_not_touch_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert "oracle_lib" not in txt and "libmsdr_oracle" not in txt and "libmsdr_ref" not in txt, f
-    for f in os.listdir(os.path.join(ROOT, "include")):
-        assert "oracle" not in open(os.path.join(ROOT, "include", f), errors="ignore").read()
+    for dp, _, fs in os.walk(os.path.join(ROOT, "include")):
+        for f in fs:
+            assert "oracle" not in open(os.path.join(dp, f), errors="ignore").read(), f
