@@ -22,7 +22,8 @@ struct FirSet {
 };
 
 // Expand one (cI, cQ) table into the four polyphase sub-filters the fused kernel consumes.
-// Output layout: [kp4 chunks][4 filters A,B,C,D][4 taps] int32, KP = 4*kp4 = roundup4(T/2 + 1).
+// Output layout: [kp4 chunks][24 words]: A[4], B[4] as int32 (I branch, IMAD pipe), C[4], D[4] as double (Q branch, DFMA pipe);
+// KP = 4*kp4 = roundup4(T/2 + 1).
 // With k' = d - (KP - T/2):  A[d] = cI[2k'], B[d] = cI[2k'+1], C[d] = cQ[2k'+1], D[d] = cQ[2(k'+1)], zero outside.
 // Derivation in DESIGN.md ("Polyphase form of the fs/4 mix + FIR").
 void expand_set(const FirSet &s, std::vector<int32_t> &out, uint32_t stride_words)
@@ -35,10 +36,12 @@ void expand_set(const FirSet &s, std::vector<int32_t> &out, uint32_t stride_word
     if (kq >= 0 && kq < half) { a = s.cI[2 * kq]; b = s.cI[2 * kq + 1]; c = s.cQ[2 * kq + 1]; }
     if (kq + 1 >= 0 && kq + 1 < half) dd = s.cQ[2 * (kq + 1)];
     const int chunk = d / 4, t = d % 4;
-    out[(size_t)chunk * 16 + 0 + t] = a;
-    out[(size_t)chunk * 16 + 4 + t] = b;
-    out[(size_t)chunk * 16 + 8 + t] = c;
-    out[(size_t)chunk * 16 + 12 + t] = dd;
+    int32_t *w = out.data() + (size_t)chunk * 24;
+    w[0 + t] = a;
+    w[4 + t] = b;
+    const double cd = (double)c, ddd = (double)dd;
+    memcpy(w + 8 + 2 * t, &cd, 8);
+    memcpy(w + 16 + 2 * t, &ddd, 8);
   }
 }
 
@@ -191,7 +194,7 @@ int msdr_chain_create(msdr_chain **out, int device, uint32_t n_channels, uint32_
   chain->KPmax = kp_of_taps(max_taps);
   chain->H = hist_of_kp(chain->KPmax);
   chain->flags = flags;
-  chain->set_stride_words = chain->KPmax * 4; // kp4 chunks x 16 words
+  chain->set_stride_words = chain->KPmax / 4 * 24; // kp4 chunks x 24 words
   chain->h_mode.assign(n_channels, (uint8_t)MSDR_MODE_AM);
   chain->h_set.assign(n_channels, 0xFF);
   chain->n_uninit = n_channels;

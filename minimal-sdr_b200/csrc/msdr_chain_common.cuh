@@ -8,49 +8,54 @@ namespace msdr {
 
 __host__ __device__ inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1u) / a * a; }
 
-__device__ __forceinline__ void unpack4(const uint4 v, uint32_t *e, uint32_t *o)
+// words per 4-tap chunk of an expanded coefficient set: A[4], B[4] as int32, C[4], D[4] as double
+constexpr int kSetChunkWords = 24;
+
+// unpack 4 words (even sample | odd sample << 16): even samples as int32 for the IMAD pipe, odd ones as double for DFMA
+__device__ __forceinline__ void unpack4(const uint4 v, uint32_t *e, double *od)
 {
-  e[0] = (uint32_t)(int)(short)(v.x & 0xFFFFu); o[0] = (uint32_t)((int)v.x >> 16);
-  e[1] = (uint32_t)(int)(short)(v.y & 0xFFFFu); o[1] = (uint32_t)((int)v.y >> 16);
-  e[2] = (uint32_t)(int)(short)(v.z & 0xFFFFu); o[2] = (uint32_t)((int)v.z >> 16);
-  e[3] = (uint32_t)(int)(short)(v.w & 0xFFFFu); o[3] = (uint32_t)((int)v.w >> 16);
+  e[0] = (uint32_t)(int)(short)(v.x & 0xFFFFu); od[0] = (double)((int)v.x >> 16);
+  e[1] = (uint32_t)(int)(short)(v.y & 0xFFFFu); od[1] = (double)((int)v.y >> 16);
+  e[2] = (uint32_t)(int)(short)(v.z & 0xFFFFu); od[2] = (double)((int)v.z >> 16);
+  e[3] = (uint32_t)(int)(short)(v.w & 0xFFFFu); od[3] = (double)((int)v.w >> 16);
 }
 
-// One channel row of one tile: FIR pair + demod for lane's 2R output samples.
-//   rowW  : sign-folded raw samples of the row as words (even sample | odd sample << 16); word Hw is tile sample 0
-//   cf    : expanded taps of the row's coefficient set: per 4-tap chunk c, cf[4c+0..3] = A, B, C, D sub-filters
-//           A: I taps for odd outputs, B: I taps for even outputs, C: Q taps for odd outputs, D: Q taps for even
-//   With u = folded samples, ue[j] = u[2j], uo[j] = u[2j+1], output pair i = (n = 2i, 2i+1), KP = 4*kp4:
-//     accX[i] = sum_{d < KP} cX[d] * {ue|uo}[i - KP + 1 + d]      (exact mod 2^32, any order)
-// 4 taps x R output pairs x 4 sub-filters = 16R multiply-accumulates on a rotating register window.
+// 4 taps x R output pairs x 4 sub-filters = 16R multiply-accumulates on a rotating register window, split over TWO pipes:
+// the I branch (sub-filters A, B on the even samples) as 32-bit wrapping IMAD, the Q branch (C, D on the odd samples) as
+// DFMA.  Products are < 2^30 and at most 128 of them are summed, so the double accumulators hold the exact integer sum
+// (|sum| < 2^37 << 2^53) and its low 32 bits are the reference's wrapped accumulator.  IMAD and DFMA co-issue at 1.65x the
+// IMAD-only rate on B200 (tools/microbench/pipes.cu).
 // The window holds W = R + 4 consecutive words; logical position x lives in physical register (x + 4*ROT) % W, so
 // sliding the window by one chunk (4 words) is a change of ROT, not a register move.
 template <int R, int ROT>
-__device__ __forceinline__ void fir_chunk(uint32_t (&e)[R + 4], uint32_t (&o)[R + 4], uint32_t (&aA)[R], uint32_t (&aB)[R], uint32_t (&aC)[R],
-                                          uint32_t (&aD)[R], const int4 *__restrict__ cf)
+__device__ __forceinline__ void fir_chunk(uint32_t (&e)[R + 4], double (&od)[R + 4], uint32_t (&aA)[R], uint32_t (&aB)[R], double (&aC)[R],
+                                          double (&aD)[R], const int4 *__restrict__ cf)
 {
   constexpr int W = R + 4;
-  const int4 cA = cf[0], cB = cf[1], cC = cf[2], cD = cf[3];
+  const int4 cA = cf[0], cB = cf[1];
+  const double2 cC0 = reinterpret_cast<const double2 *>(cf)[2], cC1 = reinterpret_cast<const double2 *>(cf)[3];
+  const double2 cD0 = reinterpret_cast<const double2 *>(cf)[4], cD1 = reinterpret_cast<const double2 *>(cf)[5];
   const uint32_t ca[4] = {(uint32_t)cA.x, (uint32_t)cA.y, (uint32_t)cA.z, (uint32_t)cA.w};
   const uint32_t cb[4] = {(uint32_t)cB.x, (uint32_t)cB.y, (uint32_t)cB.z, (uint32_t)cB.w};
-  const uint32_t cc[4] = {(uint32_t)cC.x, (uint32_t)cC.y, (uint32_t)cC.z, (uint32_t)cC.w};
-  const uint32_t cd[4] = {(uint32_t)cD.x, (uint32_t)cD.y, (uint32_t)cD.z, (uint32_t)cD.w};
+  const double cc[4] = {cC0.x, cC0.y, cC1.x, cC1.y};
+  const double cd[4] = {cD0.x, cD0.y, cD1.x, cD1.y};
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      const uint32_t ev = e[(1 + r + t + 4 * ROT) % W], ov = o[(1 + r + t + 4 * ROT) % W];
+      const uint32_t ev = e[(1 + r + t + 4 * ROT) % W];
+      const double ov = od[(1 + r + t + 4 * ROT) % W];
       aA[r] = ca[t] * ev + aA[r];
+      aC[r] = fma(cc[t], ov, aC[r]);
       aB[r] = cb[t] * ev + aB[r];
-      aC[r] = cc[t] * ov + aC[r];
-      aD[r] = cd[t] * ov + aD[r];
+      aD[r] = fma(cd[t], ov, aD[r]);
     }
   }
 }
 
 // One channel row of one tile: FIR pair + demod for lane's 2R output samples.
 //   rowW  : sign-folded raw samples of the row as words (even sample | odd sample << 16); word Hw is tile sample 0
-//   cf    : expanded taps of the row's coefficient set: per 4-tap chunk c, cf[4c+0..3] = A, B, C, D sub-filters
+//   cf    : expanded taps of the row's coefficient set: per 4-tap chunk c, 6 x 16 bytes = A, B (int32), C, D (double)
 //           A: I taps for odd outputs, B: I taps for even outputs, C: Q taps for odd outputs, D: Q taps for even
 //   With u = folded samples, ue[j] = u[2j], uo[j] = u[2j+1], output pair i = (n = 2i, 2i+1), KP = 4*kp4:
 //     accX[i] = sum_{d < KP} cX[d] * {ue|uo}[i - KP + 1 + d]      (exact mod 2^32, any order)
@@ -60,46 +65,60 @@ __device__ __forceinline__ void fir_demod_row(const uint32_t *__restrict__ rowW,
 {
   static_assert(R == 8, "the rotation schedule below assumes a 12-word window (3 chunks per turn)");
   constexpr int W = R + 4;
+  constexpr int CS = kSetChunkWords / 4; // int4 per chunk
   const int i0 = lane * R;
   if (2 * i0 >= len) return;
   const uint4 *wp = reinterpret_cast<const uint4 *>(rowW + Hw + i0 - 4 * kp4);
-  uint32_t e[W], o[W];
+  uint32_t e[W];
+  double od[W];
 #pragma unroll
-  for (int g = 0; g < W / 4; ++g) unpack4(wp[g], e + 4 * g, o + 4 * g);
+  for (int g = 0; g < W / 4; ++g) unpack4(wp[g], e + 4 * g, od + 4 * g);
   wp += W / 4;
-  uint32_t aA[R], aB[R], aC[R], aD[R];
+  uint32_t aA[R], aB[R];
+  double aC[R], aD[R];
 #pragma unroll
-  for (int r = 0; r < R; ++r) aA[r] = aB[r] = aC[r] = aD[r] = 0u;
+  for (int r = 0; r < R; ++r) { aA[r] = aB[r] = 0u; aC[r] = aD[r] = 0.0; }
 
   // chunk c consumes window rotation c % 3 and then refills the 4 slots it vacated with words for chunk c + 1;
   // the refill after the very last chunk reads 4 words past the lane's window (still inside the row buffer) and is unused.
   int c = 0;
 #pragma unroll 1
   for (; c + 3 <= kp4; c += 3) {
-    fir_chunk<R, 0>(e, o, aA, aB, aC, aD, cf + 4 * c);
-    unpack4(wp[0], e + 0, o + 0);
-    fir_chunk<R, 1>(e, o, aA, aB, aC, aD, cf + 4 * c + 4);
-    unpack4(wp[1], e + 4, o + 4);
-    fir_chunk<R, 2>(e, o, aA, aB, aC, aD, cf + 4 * c + 8);
-    unpack4(wp[2], e + 8, o + 8);
+    fir_chunk<R, 0>(e, od, aA, aB, aC, aD, cf + CS * c);
+    unpack4(wp[0], e + 0, od + 0);
+    fir_chunk<R, 1>(e, od, aA, aB, aC, aD, cf + CS * (c + 1));
+    unpack4(wp[1], e + 4, od + 4);
+    fir_chunk<R, 2>(e, od, aA, aB, aC, aD, cf + CS * (c + 2));
+    unpack4(wp[2], e + 8, od + 8);
     wp += 3;
   }
   if (c < kp4) {
-    fir_chunk<R, 0>(e, o, aA, aB, aC, aD, cf + 4 * c);
+    fir_chunk<R, 0>(e, od, aA, aB, aC, aD, cf + CS * c);
     if (c + 1 < kp4) {
-      unpack4(wp[0], e + 0, o + 0);
-      fir_chunk<R, 1>(e, o, aA, aB, aC, aD, cf + 4 * c + 4);
+      unpack4(wp[0], e + 0, od + 0);
+      fir_chunk<R, 1>(e, od, aA, aB, aC, aD, cf + CS * (c + 1));
     }
   }
 
   // arm_fir_fast_q15.c:234-238: acc >> 15, SSAT16; then the demodulation switch (Minimal-SDR.ino:589-628)
   uint32_t outw[R];
+  if (kind < 2) { // SSB: out = (int16)(I -/+ Q), two samples per word
+    const int sgn = kind ? 1 : -1;
 #pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const int Io = ssat16((int)aA[r] >> 15), Ie = ssat16((int)aB[r] >> 15);
-    const int Qo = ssat16((int)aC[r] >> 15), Qe = ssat16((int)aD[r] >> 15);
-    const int se = demod_sample(kind, Ie, Qe), so = demod_sample(kind, Io, Qo);
-    outw[r] = ((uint32_t)se & 0xFFFFu) | ((uint32_t)so << 16);
+    for (int r = 0; r < R; ++r) {
+      const int Io = ssat16((int)aA[r] >> 15), Ie = ssat16((int)aB[r] >> 15);
+      // exact integer in a double -> its value mod 2^32: low word of (x + 1.5 * 2^52)
+      const int Qo = ssat16(__double2loint(aC[r] + kBqM) >> 15), Qe = ssat16(__double2loint(aD[r] + kBqM) >> 15);
+      outw[r] = ((uint32_t)(Ie + sgn * Qe) & 0xFFFFu) | ((uint32_t)(Io + sgn * Qo) << 16);
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int Io = ssat16((int)aA[r] >> 15), Ie = ssat16((int)aB[r] >> 15);
+      const int Qo = ssat16(__double2loint(aC[r] + kBqM) >> 15), Qe = ssat16(__double2loint(aD[r] + kBqM) >> 15);
+      const int se = demod_envelope(kind, Ie, Qe), so = demod_envelope(kind, Io, Qo);
+      outw[r] = ((uint32_t)se & 0xFFFFu) | ((uint32_t)so << 16);
+    }
   }
   uint4 *dp = reinterpret_cast<uint4 *>(drow + i0);
 #pragma unroll

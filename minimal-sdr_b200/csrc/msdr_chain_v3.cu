@@ -13,18 +13,21 @@
 //
 //   warp 0          producer   claims FIR tiles (channel group g of 32, time tile i of 512 samples) from a global counter,
 //                              time-major, and streams halo + tile HBM -> smem with cp.async.bulk (TMA engine, UBLKCP).
-//   9 FIR warps     FIR        fold the fs/4 oscillator sign in place, then one channel row per warp at a time: lane l
+//   8 FIR warps     FIR        fold the fs/4 oscillator sign in place, then one channel row per warp at a time: lane l
 //                              computes 16 consecutive outputs of all four polyphase sub-filters from a rotating
 //                              register window (msdr_chain_common.cuh), >>15, SSAT, demod -> smem.
-//   warp 12         store      bulk-copies the demodulated tile smem -> `out` (used as the intermediate buffer: it is
+//   warp 11         store      bulk-copies the demodulated tile smem -> `out` (used as the intermediate buffer: it is
 //                              rewritten in place by the biquad), then publishes flag[g][i] = epoch (release).
 //   chain A, B      chains     the CTA owns channel group g = wave * grid + blockIdx for the WHOLE launch (lane = channel, state
 //                              in registers).  A two-warp stage pipeline over 128-sample sub-tiles: warp A acquires the tile
 //                              flag, bulk-loads the 32 rows from `out` (L2-hot), runs biquad object 1 in smem and hands the
 //                              buffer to warp B, which runs object 2 and bulk-stores the final audio in place.
 //
-// Warp -> scheduler placement is deliberate (warp id % 4 selects the SM sub-partition): the latency-critical chain warps
-// share sub-partition 0 with the two light I/O warps only; the nine FIR warps saturate the IMAD pipes of sub-partitions 1-3.
+// Warp -> scheduler placement is deliberate (warp id % 4 selects the SM sub-partition, tools/microbench/placement.cu):
+// the latency-critical chain warps share sub-partition 0 with the two sleeping I/O warps only (an IMAD-saturating
+// neighbour on the same sub-partition costs a chain +30..150 %, on another one nothing); the eight FIR warps own
+// sub-partitions 1-3 (with the sleeping store warp) and drive BOTH their IMAD and DFMA pipes.  12 warps keep 170 registers
+// per thread available to the FIR inner loop.
 //
 // FIR tiles of any group are produced by any SM, so FIR work balances for any channel count; chains are pinned, so no
 // state ever migrates and FIR warps never wait for a biquad.  Groups are taken in waves of `grid` chains so that a
@@ -35,14 +38,14 @@ namespace msdr {
 namespace v3 {
 
 constexpr int TT = 512;            // FIR tile, samples
-constexpr int NF = 9;              // FIR warps (warp ids 1,2,3,5,6,7,9,10,11)
-constexpr int NSLOT = 4;           // chain sub-tile ring
-constexpr int SUB = 128;           // biquad sub-tile = one AudioStream block
+constexpr int NF = 8;              // FIR warps (warp ids 1,2,3,5,6,7,9,10: sub-partitions 1-3)
+constexpr int NSLOT = 3;           // chain sub-tile ring
+constexpr int SUB = 256;           // chain sub-tile, samples (per-sub-tile fixed costs ~2 us: fewer, larger sub-tiles)
 constexpr int R = TT / 64;         // output pairs per FIR lane
 constexpr int DW = TT / 2 + 4;     // demod row pitch, words (4 mod 32: conflict-free row-wise LDS.128)
-constexpr int BW = SUB / 2 + 4;    // chain buffer row pitch, words (68 = 4 * 17, 17 odd: conflict-free)
-constexpr int kProducerWarp = 0, kChainA = 4, kChainB = 8, kStoreWarp = 12;
-constexpr int kThreads = 13 * 32;
+constexpr int BW = SUB / 2 + 4;    // chain buffer row pitch, words (132 = 4 * 33, 33 odd: conflict-free row-wise LDS.128)
+constexpr int kProducerWarp = 0, kChainA = 4, kChainB = 8, kStoreWarp = 11;
+constexpr int kThreads = 12 * 32;
 
 struct Tile {
   int grp, tile, t0, len;
@@ -112,7 +115,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
   extern __shared__ __align__(128) unsigned char smem[];
   Ctrl *pc = reinterpret_cast<Ctrl *>(smem);
   int32_t *s_sets = reinterpret_cast<int32_t *>(smem + kCtrlBytes);
-  const uint32_t sets_words = p.n_sets * p.set_stride_words;
+  const uint32_t sets_words = p.sets_in_smem ? p.n_sets * p.set_stride_words : 0u;
   const uint32_t RS = p.H + TT; // raw row pitch, samples
   unsigned char *raw_base = smem + kCtrlBytes + align_up(sets_words * 4u, 128u);
   const uint32_t raw_stage = raw_stage_bytes(p.H);
@@ -140,7 +143,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
 
   const int Hw = (int)(p.H >> 1);
 
-  const bool is_fir = (warp & 3) != 0;
+  const bool is_fir = (warp & 3) != 0 && warp != kStoreWarp;
   if (warp == kProducerWarp) {
     // ------------------------------------------------------------------ producer
     uint32_t it = 0;
@@ -214,19 +217,6 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
       }
       const int nrows = min(kGroup, (int)p.C - td.grp * kGroup);
       uint32_t *rawW = reinterpret_cast<uint32_t *>(raw_base + (uint32_t)s * raw_stage);
-      { // fold the fs/4 oscillator sign: samples with n % 4 in {2,3} are negated (Minimal-SDR.ino:550,555) = every odd word
-        const int q4 = (int)((p.H + (uint32_t)td.len) >> 3); // uint4 per row
-        for (int r = fidx; r < nrows; r += NF) {
-          uint4 *pw = reinterpret_cast<uint4 *>(rawW + (uint32_t)r * (RS >> 1));
-          for (int c4 = lane; c4 < q4; c4 += 32) {
-            uint4 v = pw[c4];
-            v.y = neg16x2(v.y);
-            v.w = neg16x2(v.w);
-            pw[c4] = v;
-          }
-        }
-      }
-      named_bar_sync(1, NF * 32);
       mbar_wait(&pc->dfree[s], ph ^ 1u);
       if (ftid == 0) pc->ddesc[s] = td;
       uint32_t *dW = reinterpret_cast<uint32_t *>(d_base + (uint32_t)s * kDStage);
@@ -238,8 +228,24 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
         const uint32_t ri = pc->rowinfo[s][job];
         const uint32_t set = ri & 0xFFu;
         const int kind = demod_kind_of((int)((ri >> 8) & 0xFFu), p.am_q31);
-        const int4 *cf = reinterpret_cast<const int4 *>(s_sets + set * p.set_stride_words);
-        fir_demod_row<R>(rawW + (uint32_t)job * (RS >> 1), cf, (int)(ri >> 16), Hw, lane, td.len, kind, dW + (uint32_t)job * DW);
+        { // fold the fs/4 oscillator sign into this row: samples with n % 4 in {2,3} are negated (Minimal-SDR.ino:550,555),
+          // i.e. every odd word.  Only this warp reads the row, so a warp-level sync is enough.
+          uint4 *pw = reinterpret_cast<uint4 *>(rawW + (uint32_t)job * (RS >> 1));
+          const int q4 = (int)((p.H + (uint32_t)td.len) >> 3); // uint4 per row
+          for (int c4 = lane; c4 < q4; c4 += 32) {
+            uint4 v = pw[c4];
+            v.y = neg16x2(v.y);
+            v.w = neg16x2(v.w);
+            pw[c4] = v;
+          }
+          __syncwarp();
+        }
+        // taps normally sit in shared memory; many long tables (e.g. ten 256-tap sets) stay in global memory and stream
+        // through L1.  One generic pointer keeps a single copy of the FIR code in the instruction cache.
+        const int4 *cf = p.sets_in_smem ? reinterpret_cast<const int4 *>(s_sets + set * p.set_stride_words)
+                                        : reinterpret_cast<const int4 *>(p.sets + (size_t)set * p.set_stride_words);
+        if (!(p.ablate & 1u))
+          fir_demod_row<R>(rawW + (uint32_t)job * (RS >> 1), cf, (int)(ri >> 16), Hw, lane, td.len, kind, dW + (uint32_t)job * DW);
       }
       fence_proxy_async_smem(); // raw[s] and d[s] were written through the generic proxy; the TMA engine touches both next
       __syncwarp();
@@ -271,11 +277,11 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
         mbar_arrive(&pc->dfree[s]);
       }
     }
-  } else {
+  } else if (warp == kChainA || warp == kChainB) {
     // ------------------------------------------------------------------ biquad chain: warp A = object 1, warp B = object 2
     const bool isA = (warp == kChainA);
     const int obj = isA ? 0 : 1;
-    const int nsub = (int)(p.L / SUB);
+    const int nsub = (int)((p.L + SUB - 1) / SUB); // the last sub-tile may be 128 samples short
     uint32_t pos = 0; // sub-tiles handled so far by this CTA's chain (ring position; identical in A and B)
     for (int g = (int)blockIdx.x; g < (int)p.NG; g += (int)p.W) {
       const uint32_t row = (uint32_t)(g * kGroup + lane);
@@ -296,16 +302,17 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
       uint32_t fl = 0u;
       if (fast && active) bq_load_stage(st[0], fl, p.bq, p.Cpad, obj, 0, ch);
 
-      auto run_object = [&](uint4 *myrow) {
+      auto run_object = [&](uint4 *myrow, int nq) {
+        if (p.ablate & 2u) return;
         if (fast) {
-          if (active) chain_span<1>(st, myrow, 0, SUB / 8);
+          if (active) chain_span<1>(st, myrow, 0, nq);
         } else { // generic cascade: stage-major over the sub-tile like the reference (filter_biquad.cpp:44-79); state in global
           for (int j = 0; j < nmax; ++j) {
             if (active && j < nst) {
               BQ gs[1];
               uint32_t gf;
               bq_load_stage(gs[0], gf, p.bq, p.Cpad, obj, j, ch);
-              chain_span<1>(gs, myrow, 0, SUB / 8);
+              chain_span<1>(gs, myrow, 0, nq);
               bq_store_stage(gs[0], gf, p.bq, p.Cpad, obj, j, ch);
             }
           }
@@ -339,26 +346,28 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
           return true;
         };
         for (int k = 0; k < nsub; ++k) {
-          // keep up to two sub-tiles in flight beyond the one being processed
-          while (ji < nsub && ji <= k + 2) {
+          // keep NSLOT - 2 sub-tiles in flight beyond the one being processed (one slot is with warp B)
+          while (ji < nsub && ji <= k + NSLOT - 2) {
             const bool must = (ji == k);
             const uint32_t pj = pos + (uint32_t)(ji - k);
-            const int sj = (int)(pj & (NSLOT - 1));
+            const int sj = (int)(pj % NSLOT);
             const uint32_t phj = (pj / NSLOT) & 1u;
             if (!tile_ready((ji * SUB) / TT, must)) break;
             if (must) mbar_wait(&pc->slot_free[sj], phj ^ 1u);
             else if (!mbar_test_wait(&pc->slot_free[sj], phj ^ 1u)) break;
-            if (lane == 0) mbar_arrive_expect_tx(&pc->ld_full[sj], (uint32_t)nrows * SUB * 2u);
+            const uint32_t lenj = min((uint32_t)SUB, p.L - (uint32_t)ji * SUB);
+            if (lane == 0) mbar_arrive_expect_tx(&pc->ld_full[sj], (uint32_t)nrows * lenj * 2u);
             __syncwarp();
             if (active)
-              bulk_g2s(reinterpret_cast<uint32_t *>(bq_base + (uint32_t)sj * kBqBuf) + (uint32_t)lane * BW, orow + (size_t)ji * SUB, SUB * 2u,
+              bulk_g2s(reinterpret_cast<uint32_t *>(bq_base + (uint32_t)sj * kBqBuf) + (uint32_t)lane * BW, orow + (size_t)ji * SUB, lenj * 2u,
                        &pc->ld_full[sj]);
             ++ji;
           }
-          const int slot = (int)(pos & (NSLOT - 1));
+          const int slot = (int)(pos % NSLOT);
           const uint32_t phs = (pos / NSLOT) & 1u;
           mbar_wait(&pc->ld_full[slot], phs);
-          run_object(reinterpret_cast<uint4 *>(reinterpret_cast<uint32_t *>(bq_base + (uint32_t)slot * kBqBuf) + (uint32_t)lane * BW));
+          run_object(reinterpret_cast<uint4 *>(reinterpret_cast<uint32_t *>(bq_base + (uint32_t)slot * kBqBuf) + (uint32_t)lane * BW),
+                     (int)(min((uint32_t)SUB, p.L - (uint32_t)k * SUB) >> 3));
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(&pc->ab_full[slot]);
@@ -366,24 +375,25 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
         }
       } else {
         for (int k = 0; k < nsub; ++k) {
-          const int slot = (int)(pos & (NSLOT - 1));
+          const int slot = (int)(pos % NSLOT);
           const uint32_t phs = (pos / NSLOT) & 1u;
           mbar_wait(&pc->ab_full[slot], phs);
           uint32_t *myrow = reinterpret_cast<uint32_t *>(bq_base + (uint32_t)slot * kBqBuf) + (uint32_t)lane * BW;
-          run_object(reinterpret_cast<uint4 *>(myrow));
+          const uint32_t lenk = min((uint32_t)SUB, p.L - (uint32_t)k * SUB);
+          run_object(reinterpret_cast<uint4 *>(myrow), (int)(lenk >> 3));
           fence_proxy_async_smem();
-          if (active) bulk_s2g(orow + (size_t)k * SUB, myrow, SUB * 2u);
+          if (active) bulk_s2g(orow + (size_t)k * SUB, myrow, lenk * 2u);
           bulk_commit();
           if (k > 0) { // the previous sub-tile's copy has finished reading its slot by now
             bulk_wait_read<1>();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&pc->slot_free[(pos - 1u) & (NSLOT - 1)]);
+            if (lane == 0) mbar_arrive(&pc->slot_free[(pos - 1u) % NSLOT]);
           }
           ++pos;
         }
         bulk_wait_read<0>();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&pc->slot_free[(pos - 1u) & (NSLOT - 1)]);
+        if (lane == 0) mbar_arrive(&pc->slot_free[(pos - 1u) % NSLOT]);
       }
 
       if (fast && active) bq_store_stage(st[0], fl, p.bq, p.Cpad, obj, 0, ch);
@@ -434,8 +444,17 @@ cudaError_t launch_chain_v3(const ChainParams &p_in, cudaStream_t stream, int va
   p.NT = (p.L + TT - 1) / TT;
   p.n_items = p.NG * p.NT;
   p.TPS = p.S = 0;
+  p.ablate = ((uint32_t)variant >> 4) & 3u; // variant bits 4,5: ablation study
 
-  const size_t smem = smem_bytes(p.H, p.n_sets, p.set_stride_words);
+  int smem_max = 0;
+  e = cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (e != cudaSuccess) return e;
+  p.sets_in_smem = 1;
+  size_t smem = smem_bytes(p.H, p.n_sets, p.set_stride_words);
+  if (smem > (size_t)smem_max) {
+    p.sets_in_smem = 0;
+    smem = smem_bytes(p.H, 0, 0);
+  }
   // variant bit 0: biquad products on DFMA (FP64 pipe) instead of IMAD.HI (integer pipe); with the chain warps alone on
   // their sub-partition the integer form has the shorter recurrence (tools/microbench/placement.cu)
   auto kern = (variant & 1) ? chain_kernel<BqStageD> : chain_kernel<BqStage>;
@@ -457,8 +476,7 @@ cudaError_t launch_chain_v3(const ChainParams &p_in, cudaStream_t stream, int va
 
 cudaError_t launch_chain(const ChainParams &p, cudaStream_t stream, int variant, ChainLaunchInfo *info)
 {
-  // variant bit 1 selects the earlier hand-off kernel (msdr_chain_kernel.cu), kept for comparison
-  return (variant & 2) ? launch_chain_handoff(p, stream, variant, info) : launch_chain_v3(p, stream, variant, info);
+  return launch_chain_v3(p, stream, variant, info);
 }
 
 } // namespace msdr

@@ -39,7 +39,9 @@ struct ChainParams {
   int *ctrl;              // [0] work counter, [1 + g] segments completed for group g (hand-off kernel)
   int *tile_flags;        // [NG][NT] == epoch once the demodulated tile is in `out` (chain kernel v3)
   uint32_t epoch;         // launch counter, never 0
-  uint32_t W;             // biquad chains per wave = grid * chains per CTA (v3)
+  uint32_t W;             // biquad chains per wave = grid (v3)
+  uint32_t ablate;        // study only: bit 0 skip the FIR arithmetic, bit 1 skip the biquad arithmetic (results are wrong)
+  uint32_t sets_in_smem;  // 0: the tap tables do not fit next to the tile buffers and are read from global memory
   uint32_t am_q31;
 };
 
@@ -51,10 +53,8 @@ struct ChainLaunchInfo {
 
 // Fused mix + FIR pair + demod + biquad cascade (K1). variant: 0 = default.
 cudaError_t launch_chain(const ChainParams &p, cudaStream_t stream, int variant, ChainLaunchInfo *info);
-cudaError_t launch_chain_handoff(const ChainParams &p, cudaStream_t stream, int variant, ChainLaunchInfo *info);
 cudaError_t launch_chain_v3(const ChainParams &p, cudaStream_t stream, int variant, ChainLaunchInfo *info);
 uint32_t chain_tile_samples();
-size_t chain_smem_bytes(uint32_t H, uint32_t n_sets, uint32_t set_stride_words, int tile);
 
 // stage-level kernels on device buffers
 cudaError_t launch_mix_fs4(const int16_t *in, int16_t *I, int16_t *Q, uint32_t rows, uint32_t n, size_t stride, cudaStream_t s);

@@ -15,17 +15,20 @@ __global__ void __launch_bounds__(416) k(long long *cyc, int *sink, unsigned cha
   if (threadIdx.x == 0) done = 0;
   __syncthreads();
   if (is_chain) {
-    BqStage si; BqStageD sd;
+    BqStage si; BqStageD sd; BqStageH sh;
     si.b0 = 236552419 + seed; si.b1 = 473104839; si.b2 = 236552419; si.a1 = 175469220; si.a2 = -47937074;
     si.x1 = si.x2 = si.y1 = si.y2 = 0; si.res = 0;
     bq_set_coefs(sd, si.b0, si.b1, si.b2, si.a1, si.a2);
     sd.x1 = sd.x2 = sd.y1 = sd.y2 = bq_d_from_int(0); sd.res = 0;
+    bq_set_coefs(sh, si.b0, si.b1, si.b2, si.a1, si.a2);
+    sh.x1 = sh.x2 = bq_d_from_int(0); sh.y1 = sh.y2 = 0; sh.res = 0;
     int x = (threadIdx.x * 977 + seed) & 0x7fff, acc = 0;
     long long t0 = clock64();
 #pragma unroll 8
     for (int n = 0; n < STEPS; ++n) {
       x = (x * 75 + 74) & 0x7fff;
-      if (F64) { int y; bq_step(sd, bq_d_from_int(x), y); acc ^= y; }
+      if (F64 == 2) { acc ^= bq_step(sh, x); }
+      else if (F64) { int y; bq_step(sd, bq_d_from_int(x), y); acc ^= y; }
       else { acc ^= bq_step(si, x << 16); }
     }
     long long t1 = clock64();
@@ -62,7 +65,7 @@ void run(const char *name, unsigned chain_mask, unsigned load_mask, long long *d
   cudaMemcpy(h, d_cyc, sms * 16 * sizeof(long long), cudaMemcpyDeviceToHost);
   double avg = 0; int n = 0;
   for (int i = 0; i < sms * 16; ++i) if (h[i]) { avg += (double)h[i]; ++n; }
-  printf("%-58s %s chain warps %08x load warps %08x : %6.1f cycles/step\n", name, F64 ? "f64" : "int", chain_mask, load_mask, avg / n / STEPS);
+  printf("%-58s %s chain warps %08x load warps %08x : %6.1f cycles/step\n", name, F64 == 2 ? "hyb" : F64 ? "f64" : "int", chain_mask, load_mask, avg / n / STEPS);
 }
 
 int main()
@@ -72,7 +75,7 @@ int main()
   long long *d_cyc; int *d_sink;
   cudaMalloc(&d_cyc, sms * 16 * sizeof(long long)); cudaMalloc(&d_sink, (size_t)sms * 416 * sizeof(int));
   const unsigned fir9 = 0x0EEE;  // warps 1,2,3,5,6,7,9,10,11
-#define BOTH(name, cm, lm) run<1>(name, cm, lm, d_cyc, d_sink, sms); run<0>(name, cm, lm, d_cyc, d_sink, sms);
+#define BOTH(name, cm, lm) run<1>(name, cm, lm, d_cyc, d_sink, sms); run<0>(name, cm, lm, d_cyc, d_sink, sms); run<2>(name, cm, lm, d_cyc, d_sink, sms);
   BOTH("one chain warp (4), nothing else", 0x010, 0);
   BOTH("two chain warps 4,8 (same wid%4)", 0x110, 0);
   BOTH("two chain warps 4,5 (different wid%4)", 0x030, 0);
