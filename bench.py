@@ -137,8 +137,12 @@ def time_cpu(m, target_s=8.0, n_threads=0):
     """Reference C chain on the host cores over a bounded sample of the workload. Returns dict for cpu_baseline."""
     lib, kind = cpu_checker()
     K = m.load_ref_constants()
-    cores = os.cpu_count() or 1
-    n_ch = max(4, 4 * (n_threads or cores))
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        cores = os.cpu_count() or 1
+    n_threads = n_threads or cores  # explicit: torchrun exports OMP_NUM_THREADS=1, which would silently serialise the baseline
+    n_ch = max(4, 4 * n_threads)
     modes = m.synth.mixed_modes(n_ch)
     x = np.stack([m.synth.channel_stream(c % 16, modes[c], 64 * BLOCK, FS) for c in range(n_ch)])
     o = cpu_chain(lib, m, K, modes)
@@ -226,6 +230,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     C = args.channels
