@@ -40,10 +40,8 @@ namespace v3 {
 constexpr int TT = 512;            // FIR tile, samples
 constexpr int NF = 8;              // FIR warps (warp ids 1,2,3,5,6,7,9,10: sub-partitions 1-3)
 constexpr int NSLOT = 3;           // chain sub-tile ring
-constexpr int SUB = 256;           // chain sub-tile, samples (per-sub-tile fixed costs ~2 us: fewer, larger sub-tiles)
 constexpr int R = TT / 64;         // output pairs per FIR lane
 constexpr int DW = TT / 2 + 4;     // demod row pitch, words (4 mod 32: conflict-free row-wise LDS.128)
-constexpr int BW = SUB / 2 + 4;    // chain buffer row pitch, words (132 = 4 * 33, 33 odd: conflict-free row-wise LDS.128)
 constexpr int kProducerWarp = 0, kChainA = 4, kChainB = 8, kStoreWarp = 11;
 constexpr int kThreads = 12 * 32;
 
@@ -73,23 +71,29 @@ static_assert(sizeof(Ctrl) <= kCtrlBytes, "Ctrl must fit its smem slot");
 
 __host__ __device__ inline uint32_t raw_stage_bytes(uint32_t H) { return kGroup * (H + TT) * 2u; }
 constexpr uint32_t kDStage = kGroup * DW * 4u;
-constexpr uint32_t kBqBuf = kGroup * BW * 4u;
+// chain sub-tile ring: KCH * 32 rows of SUB samples.  KCH = channels per chain lane (a chain owns KCH * 32 channels):
+//   KCH = 1, SUB = 256 when channel groups are scarce (one chain per SM already covers them: BASELINE config 3),
+//   KCH = 2, SUB = 128 when there are at least two groups per SM: the second channel per lane rides in the issue slots the
+//   latency-bound recurrence leaves idle (+56 % chain throughput per SM, measured).
+// Row pitch SUB/2 + 4 words = 4 * odd: conflict-free row-wise LDS.128.  Both shapes use 52 KB.
+constexpr uint32_t kBqBuf = kGroup * (256 / 2 + 4) * 4u; // == 2 * kGroup * (128 / 2 + 4) * 4 up to 1 KB
 
 size_t smem_bytes(uint32_t H, uint32_t n_sets, uint32_t set_stride_words)
 {
-  return (size_t)kCtrlBytes + align_up(n_sets * set_stride_words * 4u, 128u) + 2u * raw_stage_bytes(H) + 2u * kDStage + (size_t)NSLOT * kBqBuf;
+  return (size_t)kCtrlBytes + align_up(n_sets * set_stride_words * 4u, 128u) + 2u * raw_stage_bytes(H) + 2u * kDStage + (size_t)NSLOT * (kBqBuf + 1024u);
 }
 
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-// item -> (group, tile): waves of W groups, time-major inside a wave
-__device__ __forceinline__ void decode_item(const ChainParams &p, int item, int &grp, int &tile)
+// item -> (group, tile): waves of KCH * W groups (= W chains), time-major inside a wave
+__device__ __forceinline__ void decode_item(const ChainParams &p, const int KCH, int item, int &grp, int &tile)
 {
-  const int per_wave = (int)(p.W * p.NT);
+  const int gw = KCH * (int)p.W; // groups per wave
+  const int per_wave = gw * (int)p.NT;
   const int wave = item / per_wave;
   const int rem = item - wave * per_wave;
-  const int g0 = wave * (int)p.W;
-  const int wcur = min((int)p.W, (int)p.NG - g0);
+  const int g0 = wave * gw;
+  const int wcur = min(gw, (int)p.NG - g0);
   tile = rem / wcur;
   grp = g0 + (rem - tile * wcur);
 }
@@ -109,9 +113,12 @@ __device__ __forceinline__ void chain_span(BQ (&st)[NS], uint4 *row, int q0, int
   }
 }
 
-template <class BQ>
+template <int KCH, class BQ>
 __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
 {
+  constexpr int SUB = KCH == 1 ? 256 : 128; // chain sub-tile, samples
+  constexpr int BW = SUB / 2 + 4;           // chain buffer row pitch, words
+  constexpr uint32_t kSlotBytes = kBqBuf + 1024u;
   extern __shared__ __align__(128) unsigned char smem[];
   Ctrl *pc = reinterpret_cast<Ctrl *>(smem);
   int32_t *s_sets = reinterpret_cast<int32_t *>(smem + kCtrlBytes);
@@ -153,7 +160,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
       item = __shfl_sync(0xffffffffu, item, 0);
       if (item >= (int)p.n_items) break;
       int grp, tile;
-      decode_item(p, item, grp, tile);
+      decode_item(p, KCH, item, grp, tile);
       const int nrows = min(kGroup, (int)p.C - grp * kGroup);
       const uint32_t row = (uint32_t)(grp * kGroup + lane); // row of in/out
       const uint32_t ch = p.ch0 + row;                      // channel of the chain object
@@ -279,51 +286,89 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
     }
   } else if (warp == kChainA || warp == kChainB) {
     // ------------------------------------------------------------------ biquad chain: warp A = object 1, warp B = object 2
+    // KCH = 2 channels per lane: the recurrence is latency-bound (~45 cycles per step for ~16 instructions), so a second,
+    // independent channel per lane rides in the idle issue slots.  A chain therefore owns a SUPER-group of 2 x 32 channels.
     const bool isA = (warp == kChainA);
     const int obj = isA ? 0 : 1;
-    const int nsub = (int)((p.L + SUB - 1) / SUB); // the last sub-tile may be 128 samples short
+    const int nsub = (int)((p.L + SUB - 1) / SUB); // the last sub-tile may be short
+    const int NSG = ((int)p.NG + KCH - 1) / KCH;
     uint32_t pos = 0; // sub-tiles handled so far by this CTA's chain (ring position; identical in A and B)
-    for (int g = (int)blockIdx.x; g < (int)p.NG; g += (int)p.W) {
-      const uint32_t row = (uint32_t)(g * kGroup + lane);
-      const uint32_t ch = p.ch0 + row;
-      const bool active = row < p.C;
-      const int nrows = min(kGroup, (int)p.C - g * kGroup);
-      int16_t *orow = p.out + (size_t)row * p.stride;
+    for (int sg = (int)blockIdx.x; sg < NSG; sg += (int)p.W) {
+      uint32_t row[KCH], ch[KCH];
+      bool active[KCH];
+      int16_t *orow[KCH];
+      int nrows_total = 0, ngrp = 0;
+#pragma unroll
+      for (int h = 0; h < KCH; ++h) {
+        const int g = sg * KCH + h;
+        row[h] = (uint32_t)(g * kGroup + lane);
+        ch[h] = p.ch0 + row[h];
+        active[h] = g < (int)p.NG && row[h] < p.C;
+        orow[h] = p.out + (size_t)row[h] * p.stride;
+        if (g < (int)p.NG) { nrows_total += min(kGroup, (int)p.C - g * kGroup); ++ngrp; }
+      }
 
       // cascade structure of this lane's object: stages run while bit31 of word 7 says another follows (filter_biquad.cpp:75,79)
-      int nst = 1;
-      if (active) {
-        for (int k = 0; k < 3 && (nst == k + 1); ++k)
-          if ((uint32_t)__ldcg(p.bq + (size_t)((obj * 4 + k) * 8 + 7) * p.Cpad + ch) & 0x80000000u) nst = k + 2;
+      int nst[KCH];
+      BQ st[KCH][1];
+      uint32_t fl[KCH];
+      bool lane_fast = true;
+#pragma unroll
+      for (int h = 0; h < KCH; ++h) {
+        nst[h] = 1;
+        fl[h] = 0u;
+        if (active[h]) {
+          for (int k = 0; k < 3 && (nst[h] == k + 1); ++k)
+            if ((uint32_t)__ldcg(p.bq + (size_t)((obj * 4 + k) * 8 + 7) * p.Cpad + ch[h]) & 0x80000000u) nst[h] = k + 2;
+        }
+        lane_fast = lane_fast && nst[h] == 1;
       }
-      const bool fast = __all_sync(0xffffffffu, nst == 1);
-      const int nmax = fast ? 1 : __reduce_max_sync(0xffffffffu, active ? nst : 0);
-      BQ st[1];
-      uint32_t fl = 0u;
-      if (fast && active) bq_load_stage(st[0], fl, p.bq, p.Cpad, obj, 0, ch);
+      const bool fast = __all_sync(0xffffffffu, lane_fast);
+#pragma unroll
+      for (int h = 0; h < KCH; ++h)
+        if (fast && active[h]) bq_load_stage(st[h][0], fl[h], p.bq, p.Cpad, obj, 0, ch[h]);
 
-      auto run_object = [&](uint4 *myrow, int nq) {
+      // buffer layout of a ring slot: [KCH][32 rows][BW words]
+      auto run_object = [&](uint32_t *slot_base, int nq) {
         if (p.ablate & 2u) return;
-        if (fast) {
-          if (active) chain_span<1>(st, myrow, 0, nq);
+        uint4 *r0 = reinterpret_cast<uint4 *>(slot_base + (uint32_t)lane * BW);
+        uint4 *r1 = reinterpret_cast<uint4 *>(slot_base + (uint32_t)((KCH - 1) * kGroup + lane) * BW);
+        if (KCH == 2 && fast && active[0] && active[KCH - 1]) {
+          // two independent recurrences interleaved word by word
+#pragma unroll 1
+          for (int q = 0; q < nq; ++q) {
+            uint4 v0 = r0[q], v1 = r1[q];
+            v0.x = bq_word<1>(st[0], v0.x); v1.x = bq_word<1>(st[KCH - 1], v1.x);
+            v0.y = bq_word<1>(st[0], v0.y); v1.y = bq_word<1>(st[KCH - 1], v1.y);
+            v0.z = bq_word<1>(st[0], v0.z); v1.z = bq_word<1>(st[KCH - 1], v1.z);
+            v0.w = bq_word<1>(st[0], v0.w); v1.w = bq_word<1>(st[KCH - 1], v1.w);
+            r0[q] = v0; r1[q] = v1;
+          }
+        } else if (fast) {
+          if (active[0]) chain_span<1>(st[0], r0, 0, nq);
+          if (KCH == 2 && active[KCH - 1]) chain_span<1>(st[KCH - 1], r1, 0, nq);
         } else { // generic cascade: stage-major over the sub-tile like the reference (filter_biquad.cpp:44-79); state in global
-          for (int j = 0; j < nmax; ++j) {
-            if (active && j < nst) {
-              BQ gs[1];
-              uint32_t gf;
-              bq_load_stage(gs[0], gf, p.bq, p.Cpad, obj, j, ch);
-              chain_span<1>(gs, myrow, 0, nq);
-              bq_store_stage(gs[0], gf, p.bq, p.Cpad, obj, j, ch);
+#pragma unroll
+          for (int h = 0; h < KCH; ++h) {
+            const int nmax = __reduce_max_sync(0xffffffffu, active[h] ? nst[h] : 0);
+            for (int j = 0; j < nmax; ++j) {
+              if (active[h] && j < nst[h]) {
+                BQ gs[1];
+                uint32_t gf;
+                bq_load_stage(gs[0], gf, p.bq, p.Cpad, obj, j, ch[h]);
+                chain_span<1>(gs, h ? r1 : r0, 0, nq);
+                bq_store_stage(gs[0], gf, p.bq, p.Cpad, obj, j, ch[h]);
+              }
             }
           }
         }
       };
 
       if (isA) {
-        const int *gflags = p.tile_flags + (size_t)g * p.NT;
-        int ready = 0; // leading FIR tiles of this group known to be in `out`
+        int ready = 0; // leading FIR tiles known to be in `out` for every group of the super-group
         int ji = 0;    // next sub-tile to load
-        // wait (or poll once) until FIR tile t is published; on success order the async-proxy reads after the acquire
+        // wait (or poll once) until FIR tile t of all member groups is published; on success order the async-proxy reads
+        // after the acquire
         auto tile_ready = [&](int t, bool blocking) -> bool {
           bool advanced = false;
           while (ready <= t) {
@@ -331,8 +376,10 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
             if (lane == 0) {
               const long long t0 = clock64();
               for (;;) {
-                if (ld_acquire_gpu(gflags + ready) == (int)p.epoch) { ok = 1; break; }
-                if (!blocking) break;
+                ok = 1;
+                for (int h = 0; h < ngrp; ++h)
+                  if (ld_acquire_gpu(p.tile_flags + (size_t)(sg * KCH + h) * p.NT + ready) != (int)p.epoch) ok = 0;
+                if (ok || !blocking) break;
                 __nanosleep(100);
                 if (clock64() - t0 > kWatchdogCycles) __trap();
               }
@@ -356,18 +403,18 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
             if (must) mbar_wait(&pc->slot_free[sj], phj ^ 1u);
             else if (!mbar_test_wait(&pc->slot_free[sj], phj ^ 1u)) break;
             const uint32_t lenj = min((uint32_t)SUB, p.L - (uint32_t)ji * SUB);
-            if (lane == 0) mbar_arrive_expect_tx(&pc->ld_full[sj], (uint32_t)nrows * lenj * 2u);
+            if (lane == 0) mbar_arrive_expect_tx(&pc->ld_full[sj], (uint32_t)nrows_total * lenj * 2u);
             __syncwarp();
-            if (active)
-              bulk_g2s(reinterpret_cast<uint32_t *>(bq_base + (uint32_t)sj * kBqBuf) + (uint32_t)lane * BW, orow + (size_t)ji * SUB, lenj * 2u,
-                       &pc->ld_full[sj]);
+            uint32_t *sb = reinterpret_cast<uint32_t *>(bq_base + (uint32_t)sj * kSlotBytes);
+#pragma unroll
+            for (int h = 0; h < KCH; ++h)
+              if (active[h]) bulk_g2s(sb + (uint32_t)(h * kGroup + lane) * BW, orow[h] + (size_t)ji * SUB, lenj * 2u, &pc->ld_full[sj]);
             ++ji;
           }
           const int slot = (int)(pos % NSLOT);
           const uint32_t phs = (pos / NSLOT) & 1u;
           mbar_wait(&pc->ld_full[slot], phs);
-          run_object(reinterpret_cast<uint4 *>(reinterpret_cast<uint32_t *>(bq_base + (uint32_t)slot * kBqBuf) + (uint32_t)lane * BW),
-                     (int)(min((uint32_t)SUB, p.L - (uint32_t)k * SUB) >> 3));
+          run_object(reinterpret_cast<uint32_t *>(bq_base + (uint32_t)slot * kSlotBytes), (int)(min((uint32_t)SUB, p.L - (uint32_t)k * SUB) >> 3));
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(&pc->ab_full[slot]);
@@ -378,11 +425,13 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
           const int slot = (int)(pos % NSLOT);
           const uint32_t phs = (pos / NSLOT) & 1u;
           mbar_wait(&pc->ab_full[slot], phs);
-          uint32_t *myrow = reinterpret_cast<uint32_t *>(bq_base + (uint32_t)slot * kBqBuf) + (uint32_t)lane * BW;
+          uint32_t *sb = reinterpret_cast<uint32_t *>(bq_base + (uint32_t)slot * kSlotBytes);
           const uint32_t lenk = min((uint32_t)SUB, p.L - (uint32_t)k * SUB);
-          run_object(reinterpret_cast<uint4 *>(myrow), (int)(lenk >> 3));
+          run_object(sb, (int)(lenk >> 3));
           fence_proxy_async_smem();
-          if (active) bulk_s2g(orow + (size_t)k * SUB, myrow, lenk * 2u);
+#pragma unroll
+          for (int h = 0; h < KCH; ++h)
+            if (active[h]) bulk_s2g(orow[h] + (size_t)k * SUB, sb + (uint32_t)(h * kGroup + lane) * BW, lenk * 2u);
           bulk_commit();
           if (k > 0) { // the previous sub-tile's copy has finished reading its slot by now
             bulk_wait_read<1>();
@@ -396,13 +445,16 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
         if (lane == 0) mbar_arrive(&pc->slot_free[(pos - 1u) % NSLOT]);
       }
 
-      if (fast && active) bq_store_stage(st[0], fl, p.bq, p.Cpad, obj, 0, ch);
+#pragma unroll
+      for (int h = 0; h < KCH; ++h)
+        if (fast && active[h]) bq_store_stage(st[h][0], fl[h], p.bq, p.Cpad, obj, 0, ch[h]);
       if (!isA) {
-        // carry the last H raw samples: hist <- tail of (hist || in[0..L)).  Every FIR tile of this group has been
+        // carry the last H raw samples: hist <- tail of (hist || in[0..L)).  Every FIR tile of these groups has been
         // published (warp B consumed them all), so nobody reads the old history any more.
         const uint32_t hq = p.H >> 3; // uint4 per history row (<= 33)
-        for (int r = 0; r < nrows; ++r) {
-          const size_t c = (size_t)(g * kGroup + r);
+        for (int r = 0; r < ngrp * kGroup; ++r) {
+          const size_t c = (size_t)sg * KCH * kGroup + (size_t)r;
+          if (c >= p.C) break;
           uint4 *hrow = reinterpret_cast<uint4 *>(p.hist + ((size_t)p.ch0 + c) * p.H);
           const uint4 *irow = reinterpret_cast<const uint4 *>(p.in + c * p.stride);
           uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
@@ -457,7 +509,12 @@ cudaError_t launch_chain_v3(const ChainParams &p_in, cudaStream_t stream, int va
   }
   // variant bit 0: biquad products on DFMA (FP64 pipe) instead of IMAD.HI (integer pipe); with the chain warps alone on
   // their sub-partition the integer form has the shorter recurrence (tools/microbench/placement.cu)
-  auto kern = (variant & 1) ? chain_kernel<BqStageD> : chain_kernel<BqStage>;
+  // channels per chain lane: 1.  The two-channel form (variant bit 3) raises a chain's own throughput by 56 % but doubles the
+  // copy skeleton per sub-tile and loses to the one-channel form on both measured shapes (4096 x 64 blocks: 43 vs 81 Gsamples/s,
+  // 65536 x 128 blocks: 93 vs 102), because the FIR warps are the other half of the bound.
+  const int kch = (variant & 8) ? 2 : 1;
+  auto kern = kch == 2 ? ((variant & 1) ? chain_kernel<2, BqStageD> : chain_kernel<2, BqStage>)
+                       : ((variant & 1) ? chain_kernel<1, BqStageD> : chain_kernel<1, BqStage>);
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int per_sm = 0;
@@ -466,7 +523,8 @@ cudaError_t launch_chain_v3(const ChainParams &p_in, cudaStream_t stream, int va
   if (per_sm < 1) return cudaErrorLaunchOutOfResources;
   // every CTA must be resident: chains spin on flags that FIR warps of other CTAs publish
   uint32_t grid = (uint32_t)sms;
-  const uint32_t need = p.n_items > p.NG ? p.n_items : p.NG;
+  const uint32_t nsg = (p.NG + (uint32_t)kch - 1) / (uint32_t)kch;
+  const uint32_t need = p.n_items > nsg ? p.n_items : nsg;
   if (grid > need) grid = need;
   p.W = grid;
   if (info) { info->grid = (int)grid; info->block = kThreads; info->smem = smem; info->tile = TT; }
