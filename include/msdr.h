@@ -160,6 +160,13 @@ int msdr_op_freq_conv(int device, int dir, int pass, int16_t *I, int16_t *Q, con
 /* arm_sqrt_q31 (arm_sqrt_q31.c:50-138) element-wise; status[i] = 0 or -1 like arm_status (may be NULL). */
 int msdr_op_sqrt_q31(int device, const int32_t *in, int32_t *out, int32_t *status, uint32_t n);
 
+/* K3 study: mix + FIR pair + demodulation on the tensor cores (tcgen05 kind::i8, byte-split Toeplitz form), no
+ * biquad, zero initial history.  n must be a multiple of 64.  kinds: per-row demod kind (as msdr_op_demod) or NULL for kind0. */
+int msdr_op_fir_demod_tc(int device, uint16_t numTaps, const int16_t *cI, const int16_t *cQ, const uint8_t *kinds, int kind0, const int16_t *in,
+                         int16_t *out, uint32_t rows, uint32_t n, size_t stride);
+/* Device-resident timing of the same kernel on pseudo-random data: milliseconds per launch over `iters` launches. */
+int msdr_study_fir_demod_tc_time(int device, uint16_t numTaps, uint32_t rows, uint32_t n, int kind0, int iters, float *ms_per_iter);
+
 const char *msdr_version(void);
 
 #ifdef __cplusplus

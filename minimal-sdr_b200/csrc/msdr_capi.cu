@@ -45,6 +45,18 @@ void expand_set(const FirSet &s, std::vector<int32_t> &out, uint32_t stride_word
   }
 }
 
+// Same sub-filters as plain ints (tensor-core study operand builder).
+void expand_set_int(uint32_t T, const int16_t *cI, const int16_t *cQ, std::vector<int> &A, std::vector<int> &B, std::vector<int> &C, std::vector<int> &D)
+{
+  const int half = (int)T / 2, KP = (int)kp_of_taps(T);
+  A.assign(KP, 0); B.assign(KP, 0); C.assign(KP, 0); D.assign(KP, 0);
+  for (int d = 0; d < KP; ++d) {
+    const int kq = d - (KP - half);
+    if (kq >= 0 && kq < half) { A[d] = cI[2 * kq]; B[d] = cI[2 * kq + 1]; C[d] = cQ[2 * kq + 1]; }
+    if (kq + 1 >= 0 && kq + 1 < half) D[d] = cQ[2 * (kq + 1)];
+  }
+}
+
 } // namespace
 
 struct msdr_chain {
@@ -612,6 +624,82 @@ int msdr_op_freq_conv(int device, int dir, int pass, int16_t *I, int16_t *Q, con
   OPCK(launch_freq_conv(dir, a.as<int16_t>(), b.as<int16_t>(), oi.as<int16_t>(), oq.as<int16_t>(), rows, n, n, nullptr));
   OPCK(cudaMemcpy2D(I, stride * 2, a.p, (size_t)n * 2, (size_t)n * 2, rows, cudaMemcpyDeviceToHost));
   OPCK(cudaMemcpy2D(Q, stride * 2, b.p, (size_t)n * 2, (size_t)n * 2, rows, cudaMemcpyDeviceToHost));
+  return MSDR_OK;
+}
+
+// K3 study operator: mix + FIR pair + demod on the tensor cores (no biquad).  kinds: per-row demod kind or NULL (kind0 for all).
+int msdr_op_fir_demod_tc(int device, uint16_t numTaps, const int16_t *cI, const int16_t *cQ, const uint8_t *kinds, int kind0, const int16_t *in,
+                         int16_t *out, uint32_t rows, uint32_t n, size_t stride)
+{
+  if ((numTaps & 1u) || numTaps < 4 || numTaps > MSDR_MAX_TAPS) return MSDR_ERR_ARGUMENT;
+  if (!cI || !cQ || !in || !out || n > stride || (n % tc_tile_samples()) || kind0 < 0 || kind0 > 3) return MSDR_ERR_ARGUMENT;
+  int st = op_begin(device); if (st) return st;
+  const uint32_t K = tc_window_words(numTaps), KP = kp_of_taps(numTaps);
+  const uint32_t pad = 2 * (K - tc_tile_samples() / 2); // samples of (zero) history in front of every row
+  const size_t dstride = (size_t)pad + n;
+  std::vector<int> A, B, C, D;
+  expand_set_int(numTaps, cI, cQ, A, B, C, D);
+  std::vector<uint8_t> bm((size_t)4 * tc_tile_samples() * K);
+  tc_build_bmat(A.data(), B.data(), C.data(), D.data(), KP, K, bm.data());
+  std::vector<uint8_t> hk(rows, (uint8_t)kind0), hs(rows, 0);
+  if (kinds) memcpy(hk.data(), kinds, rows);
+  DevBuf din, dout, dbm, dk, ds;
+  OPCK(din.alloc(rows * dstride * 2)); OPCK(dout.alloc((size_t)rows * n * 2)); OPCK(dbm.alloc(bm.size())); OPCK(dk.alloc(rows)); OPCK(ds.alloc(rows));
+  OPCK(cudaMemset(din.p, 0, rows * dstride * 2));
+  OPCK(cudaMemcpy2D(din.as<int16_t>() + pad, dstride * 2, in, stride * 2, (size_t)n * 2, rows, cudaMemcpyHostToDevice));
+  OPCK(cudaMemcpy(dbm.p, bm.data(), bm.size(), cudaMemcpyHostToDevice));
+  OPCK(cudaMemcpy(dk.p, hk.data(), rows, cudaMemcpyHostToDevice));
+  OPCK(cudaMemcpy(ds.p, hs.data(), rows, cudaMemcpyHostToDevice));
+  OPCK(launch_fir_demod_tc(din.as<int16_t>() + pad, dstride, dout.as<int16_t>(), n, rows, n, K, dbm.as<uint8_t>(), ds.as<uint8_t>(), dk.as<uint8_t>(), nullptr));
+  OPCK(cudaDeviceSynchronize());
+  OPCK(cudaMemcpy2D(out, stride * 2, dout.p, (size_t)n * 2, (size_t)n * 2, rows, cudaMemcpyDeviceToHost));
+  return MSDR_OK;
+}
+
+// K3 study timing: device-resident pseudo-random input, `iters` launches timed with CUDA events; returns ms per launch.
+int msdr_study_fir_demod_tc_time(int device, uint16_t numTaps, uint32_t rows, uint32_t n, int kind0, int iters, float *ms_per_iter)
+{
+  if ((numTaps & 1u) || numTaps < 4 || numTaps > MSDR_MAX_TAPS || !ms_per_iter || (n % tc_tile_samples()) || iters < 1) return MSDR_ERR_ARGUMENT;
+  int st = op_begin(device); if (st) return st;
+  const uint32_t K = tc_window_words(numTaps), KP = kp_of_taps(numTaps);
+  const uint32_t pad = 2 * (K - tc_tile_samples() / 2);
+  const size_t dstride = (size_t)pad + n;
+  std::vector<int16_t> cI(numTaps), cQ(numTaps);
+  uint32_t lcg = 12345u;
+  for (uint32_t i = 0; i < numTaps; ++i) { lcg = lcg * 1664525u + 1013904223u; cI[i] = (int16_t)((int)(lcg >> 20) - 2048); cQ[numTaps - 1 - i] = cI[i]; }
+  std::vector<int> A, B, C, D;
+  expand_set_int(numTaps, cI.data(), cQ.data(), A, B, C, D);
+  std::vector<uint8_t> bm((size_t)4 * tc_tile_samples() * K);
+  tc_build_bmat(A.data(), B.data(), C.data(), D.data(), KP, K, bm.data());
+  std::vector<int16_t> hrow(dstride);
+  for (size_t i = 0; i < dstride; ++i) { lcg = lcg * 1664525u + 1013904223u; hrow[i] = (int16_t)(lcg >> 16); }
+  DevBuf din, dout, dbm, dk, ds;
+  OPCK(din.alloc(rows * dstride * 2)); OPCK(dout.alloc((size_t)rows * n * 2)); OPCK(dbm.alloc(bm.size())); OPCK(dk.alloc(rows)); OPCK(ds.alloc(rows));
+  { // the same row pattern everywhere is fine for timing (no data-dependent work): upload 64 rows, replicate on the device
+    const uint32_t rep = std::min<uint32_t>(64, rows);
+    std::vector<int16_t> blockrows((size_t)rep * dstride);
+    for (uint32_t r = 0; r < rep; ++r) memcpy(blockrows.data() + (size_t)r * dstride, hrow.data(), dstride * 2);
+    OPCK(cudaMemcpy(din.p, blockrows.data(), blockrows.size() * 2, cudaMemcpyHostToDevice));
+    for (uint32_t r = rep; r < rows; r += rep)
+      OPCK(cudaMemcpy(din.as<int16_t>() + (size_t)r * dstride, din.p, (size_t)std::min(rep, rows - r) * dstride * 2, cudaMemcpyDeviceToDevice));
+  }
+  OPCK(cudaMemcpy(dbm.p, bm.data(), bm.size(), cudaMemcpyHostToDevice));
+  OPCK(cudaMemset(dk.p, kind0, rows));
+  OPCK(cudaMemset(ds.p, 0, rows));
+  cudaEvent_t e0, e1;
+  OPCK(cudaEventCreate(&e0)); OPCK(cudaEventCreate(&e1));
+  for (int w = 0; w < 3; ++w)
+    OPCK(launch_fir_demod_tc(din.as<int16_t>() + pad, dstride, dout.as<int16_t>(), n, rows, n, K, dbm.as<uint8_t>(), ds.as<uint8_t>(), dk.as<uint8_t>(), nullptr));
+  OPCK(cudaDeviceSynchronize());
+  OPCK(cudaEventRecord(e0, nullptr));
+  for (int it = 0; it < iters; ++it)
+    OPCK(launch_fir_demod_tc(din.as<int16_t>() + pad, dstride, dout.as<int16_t>(), n, rows, n, K, dbm.as<uint8_t>(), ds.as<uint8_t>(), dk.as<uint8_t>(), nullptr));
+  OPCK(cudaEventRecord(e1, nullptr));
+  OPCK(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  OPCK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  *ms_per_iter = ms / (float)iters;
   return MSDR_OK;
 }
 

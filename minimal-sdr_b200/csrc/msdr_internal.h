@@ -64,6 +64,13 @@ cudaError_t launch_demod(int kind, const int16_t *I, const int16_t *Q, int16_t *
 cudaError_t launch_biquad(int32_t *definition, int16_t *data, uint32_t rows, uint32_t n, size_t stride, cudaStream_t s);
 cudaError_t launch_freq_conv(int dir, int16_t *I, int16_t *Q, const int16_t *oscI, const int16_t *oscQ, uint32_t rows, uint32_t n, size_t stride,
                              cudaStream_t s);
+// K3 study: tensor-core FIR + demod (msdr_fir_tc.cu)
+uint32_t tc_window_words(uint32_t T);
+uint32_t tc_tile_samples();
+uint32_t tc_tile_rows();
+void tc_build_bmat(const int *cA, const int *cB, const int *cC, const int *cD, uint32_t KP, uint32_t K, uint8_t *out);
+cudaError_t launch_fir_demod_tc(const int16_t *in, size_t stride, int16_t *out, size_t ostride, uint32_t rows, uint32_t L, uint32_t K, const uint8_t *bmat,
+                                const uint8_t *row_set, const uint8_t *row_kind, cudaStream_t s);
 cudaError_t launch_sqrt_q31(const int32_t *in, int32_t *out, int32_t *status, uint32_t n, cudaStream_t s);
 cudaError_t launch_bq_setcoef(int32_t *bq, uint32_t Cpad, int object, uint32_t ch0, uint32_t nch, uint32_t stage, const int32_t coef[5], cudaStream_t s);
 
