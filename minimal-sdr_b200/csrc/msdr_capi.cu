@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -88,6 +89,19 @@ struct msdr_chain {
   int16_t *pin_in = nullptr, *pin_out = nullptr;
   size_t pin_samples = 0;
 
+  // tensor-core FIR plan (chain kernel v4): rows sorted by tap table inside each wave of chains, see build_tc_plan()
+  uint64_t meta_version = 1;  // bumped whenever a channel's table binding or a table's contents change
+  struct TcPlan {
+    uint64_t version = 0;
+    uint32_t ch0 = 0, nch = 0, W = 0, K = 0, ring = 0, n_rb = 0, n_waves = 0;
+    bool usable = false;
+    uint32_t *d_rowmap = nullptr, *d_grp = nullptr, *d_wave_rb0 = nullptr;
+    uint4 *d_rb = nullptr;
+    uint8_t *d_bmat = nullptr;
+  } plan;
+  int *d_tile_cnt = nullptr;
+  size_t tile_cnt_len = 0;
+
   int variant = 0;
   uint32_t host_chunk_channels = 0, host_chunk_blocks = 0; // 0 = auto
   uint64_t launches = 0;
@@ -123,6 +137,7 @@ int upload_set(msdr_chain *chain, uint32_t id)
                      chain->stream));
   CK(cudaMemcpyAsync(chain->d_set_kp4 + id, &kp4, sizeof(kp4), cudaMemcpyHostToDevice, chain->stream));
   CK(cudaStreamSynchronize(chain->stream)); // `ex` and `kp4` are stack/heap temporaries
+  chain->meta_version++;
   return MSDR_OK;
 }
 
@@ -158,6 +173,7 @@ int assign_set(msdr_chain *chain, uint32_t ch0, uint32_t nch, uint32_t id)
     chain->h_set[c] = (uint8_t)id;
   }
   chain->sets[id].users += nch;
+  chain->meta_version++;
   CK(cudaMemcpyAsync(chain->d_set + ch0, chain->h_set.data() + ch0, nch, cudaMemcpyHostToDevice, chain->stream));
   CK(cudaStreamSynchronize(chain->stream));
   return MSDR_OK;
@@ -210,6 +226,7 @@ int msdr_chain_create(msdr_chain **out, int device, uint32_t n_channels, uint32_
   chain->h_mode.assign(n_channels, (uint8_t)MSDR_MODE_AM);
   chain->h_set.assign(n_channels, 0xFF);
   chain->n_uninit = n_channels;
+  if (const char *ev = getenv("MSDR_VARIANT")) chain->variant = atoi(ev); // developer aid: default kernel variant
 
   auto bail = [&](cudaError_t ee, const char *what) {
     int st = cuda_fail(nullptr, ee, what);
@@ -248,6 +265,8 @@ void msdr_chain_destroy(msdr_chain *chain)
   cudaSetDevice(chain->device);
   if (chain->stream) cudaStreamSynchronize(chain->stream);
   cudaFree(chain->d_mode); cudaFree(chain->d_set); cudaFree(chain->d_hist); cudaFree(chain->d_bq);
+  cudaFree(chain->plan.d_rowmap); cudaFree(chain->plan.d_grp); cudaFree(chain->plan.d_wave_rb0); cudaFree(chain->plan.d_rb); cudaFree(chain->plan.d_bmat);
+  cudaFree(chain->d_tile_cnt);
   cudaFree(chain->d_sets); cudaFree(chain->d_set_kp4); cudaFree(chain->d_ctrl); cudaFree(chain->d_tile_flags);
   cudaFree(chain->d_in); cudaFree(chain->d_out);
   if (chain->pin_in) cudaFreeHost(chain->pin_in);
@@ -343,6 +362,89 @@ int msdr_biquad_set_coefficients(msdr_chain *chain, int object, uint32_t ch0, ui
   return MSDR_OK;
 }
 
+namespace {
+
+void free_tc_plan(msdr_chain *chain)
+{
+  msdr_chain::TcPlan &pl = chain->plan;
+  cudaFree(pl.d_rowmap); cudaFree(pl.d_grp); cudaFree(pl.d_wave_rb0); cudaFree(pl.d_rb); cudaFree(pl.d_bmat);
+  pl = msdr_chain::TcPlan{};
+}
+
+// Row plan of the tensor-core chain kernel for the channel range [ch0, ch0 + nch).  All 128 rows of a GEMM tile share the
+// B operand, i.e. one tap table, and a chain wave (W groups of 32 channels, one per CTA) must get its FIR input first; so
+// inside each wave the rows are sorted by table and cut into blocks of 128 (the last block of a table is padded).
+// Every block lists the channel groups it contributes to and with how many rows: the epilogue adds those counts to
+// tile_cnt[group][span], a chain starts a span when the count reaches the group's row count.
+int build_tc_plan(msdr_chain *chain, uint32_t ch0, uint32_t nch, uint32_t W)
+{
+  msdr_chain::TcPlan &pl = chain->plan;
+  if (pl.version == chain->meta_version && pl.ch0 == ch0 && pl.nch == nch && pl.W == W) return MSDR_OK;
+  CK(cudaStreamSynchronize(chain->stream)); // a launch in flight may still read the old plan
+  free_tc_plan(chain);
+  pl.version = chain->meta_version; pl.ch0 = ch0; pl.nch = nch; pl.W = W;
+
+  uint32_t kp_max = 0;
+  for (uint32_t c = ch0; c < ch0 + nch; ++c) kp_max = std::max(kp_max, kp_of_taps(chain->sets[chain->h_set[c]].T));
+  const uint32_t K = tc_window_words_kp(kp_max);
+  int smem_max = 0;
+  CK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, chain->device));
+  uint32_t ring = 0;
+  if (!chain_v4_config(K, smem_max, &ring)) { pl.usable = false; return MSDR_OK; }
+  pl.K = K; pl.ring = ring;
+
+  const uint32_t NG = (nch + kGroup - 1) / kGroup, n_sets = (uint32_t)chain->sets.size(), M = tc_tile_rows();
+  std::vector<uint32_t> rowmap, grp, wave_rb0;
+  std::vector<uint4> rbs;
+  std::vector<std::vector<uint32_t>> bucket(n_sets);
+  wave_rb0.push_back(0);
+  for (uint32_t g0 = 0; g0 < NG; g0 += W) {
+    const uint32_t g1 = std::min(NG, g0 + W);
+    for (auto &b : bucket) b.clear();
+    for (uint32_t r = g0 * kGroup; r < std::min(nch, g1 * (uint32_t)kGroup); ++r) bucket[chain->h_set[ch0 + r]].push_back(r);
+    for (uint32_t sid = 0; sid < n_sets; ++sid) {
+      const std::vector<uint32_t> &rows = bucket[sid];
+      for (size_t i0 = 0; i0 < rows.size(); i0 += M) {
+        const size_t i1 = std::min(rows.size(), i0 + M);
+        const uint32_t grp_off = (uint32_t)grp.size();
+        for (size_t i = i0; i < i1; ++i) {
+          rowmap.push_back(rows[i]);
+          const uint32_t g = rows[i] / kGroup;
+          if (grp.size() > grp_off && (grp.back() & 0xFFFFFFu) == g) grp.back() += 1u << 24;
+          else grp.push_back(g | (1u << 24));
+        }
+        for (size_t i = i1; i < i0 + M; ++i) rowmap.push_back(0xFFFFFFFFu);
+        rbs.push_back(make_uint4(sid, grp_off, (uint32_t)grp.size() - grp_off, (uint32_t)wave_rb0.size() - 1));
+      }
+    }
+    wave_rb0.push_back((uint32_t)rbs.size());
+  }
+  pl.n_rb = (uint32_t)rbs.size();
+  pl.n_waves = (uint32_t)wave_rb0.size() - 1;
+
+  // Toeplitz operands of every live table for the common window K
+  const size_t bsz = (size_t)4 * tc_tile_samples() * K;
+  std::vector<uint8_t> bm(bsz * n_sets, 0);
+  for (uint32_t sid = 0; sid < n_sets; ++sid) {
+    const FirSet &fs = chain->sets[sid];
+    if (fs.users == 0 || kp_of_taps(fs.T) > kp_max) continue;
+    std::vector<int> A, B, C, D;
+    expand_set_int(fs.T, fs.cI.data(), fs.cQ.data(), A, B, C, D);
+    tc_build_bmat(A.data(), B.data(), C.data(), D.data(), kp_of_taps(fs.T), K, bm.data() + bsz * sid);
+  }
+  CK(cudaMalloc(&pl.d_rowmap, rowmap.size() * 4)); CK(cudaMalloc(&pl.d_grp, std::max<size_t>(grp.size(), 1) * 4));
+  CK(cudaMalloc(&pl.d_wave_rb0, wave_rb0.size() * 4)); CK(cudaMalloc(&pl.d_rb, rbs.size() * sizeof(uint4))); CK(cudaMalloc(&pl.d_bmat, bm.size()));
+  CK(cudaMemcpy(pl.d_rowmap, rowmap.data(), rowmap.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(pl.d_grp, grp.data(), grp.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(pl.d_wave_rb0, wave_rb0.data(), wave_rb0.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(pl.d_rb, rbs.data(), rbs.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(pl.d_bmat, bm.data(), bm.size(), cudaMemcpyHostToDevice));
+  pl.usable = true;
+  return MSDR_OK;
+}
+
+} // namespace
+
 int msdr_chain_update_range_device(msdr_chain *chain, uint32_t ch0, uint32_t nch, const int16_t *d_in, int16_t *d_out, uint32_t n_blocks,
                                    size_t stride)
 {
@@ -380,10 +482,59 @@ int msdr_chain_update_range_device(msdr_chain *chain, uint32_t ch0, uint32_t nch
   p.tile_flags = chain->d_tile_flags;
   p.epoch = ++chain->epoch;
   CK(cudaMemsetAsync(chain->d_ctrl, 0, (size_t)(1 + NG) * sizeof(int), chain->stream));
+  bool use_tc = (chain->variant & 64) == 0; // variant bit 6: force the CUDA-core FIR kernel (msdr_chain_v3.cu)
+  if (use_tc) { // tensor-core FIR producers (msdr_chain_v4.cu)
+    int sms = 0;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, chain->device));
+    int st = build_tc_plan(chain, ch0, nch, (uint32_t)sms);
+    if (st != MSDR_OK) return st;
+    const msdr_chain::TcPlan &pl = chain->plan;
+    use_tc = pl.usable;
+    if (use_tc) {
+      p.NG = NG;
+      p.NT = (p.L + chain_v4_span_samples() - 1) / chain_v4_span_samples();
+      p.W = (uint32_t)sms;
+      p.n_items = pl.n_rb * p.NT;
+      p.tc_rowmap = pl.d_rowmap; p.tc_rb = pl.d_rb; p.tc_grp = pl.d_grp; p.tc_wave_rb0 = pl.d_wave_rb0; p.tc_bmat = pl.d_bmat;
+      p.tc_K = pl.K; p.tc_ring = pl.ring;
+      const size_t n_cnt = (size_t)NG * p.NT;
+      if (n_cnt > chain->tile_cnt_len) {
+        CK(cudaStreamSynchronize(chain->stream));
+        cudaFree(chain->d_tile_cnt);
+        chain->d_tile_cnt = nullptr; chain->tile_cnt_len = 0;
+        CK(cudaMalloc(&chain->d_tile_cnt, (n_cnt + 1024) * sizeof(int)));
+        chain->tile_cnt_len = n_cnt + 1024;
+      }
+      CK(cudaMemsetAsync(chain->d_tile_cnt, 0, n_cnt * sizeof(int), chain->stream));
+      p.tile_cnt = chain->d_tile_cnt;
+    }
+  }
   if (chain->timed) CK(cudaEventRecord(chain->ev0, chain->stream));
-  CK(launch_chain(p, chain->stream, chain->variant, &chain->last_info));
+  static const bool prof_on = getenv("MSDR_PROF") != nullptr; // developer aid: per-role cycle totals of the v4 kernel on stderr
+  long long *d_prof = nullptr;
+  if (use_tc && prof_on) {
+    CK(cudaMalloc(&d_prof, (size_t)p.W * 64 * sizeof(long long)));
+    CK(cudaMemsetAsync(d_prof, 0, (size_t)p.W * 64 * sizeof(long long), chain->stream));
+    p.prof = d_prof;
+  }
+  if (use_tc) CK(launch_chain_v4(p, chain->stream, chain->variant, &chain->last_info));
+  else CK(launch_chain(p, chain->stream, chain->variant, &chain->last_info));
   if (chain->timed) CK(cudaEventRecord(chain->ev1, chain->stream));
   chain->launches++;
+  if (d_prof) {
+    std::vector<long long> h((size_t)p.W * 64);
+    CK(cudaMemcpyAsync(h.data(), d_prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, chain->stream));
+    CK(cudaStreamSynchronize(chain->stream));
+    cudaFree(d_prof);
+    static const char *role[7] = {"convert", "mma", "epilogue", "chainA", "chainB", "load", "store"};
+    fprintf(stderr, "[msdr prof] grid %u, mean cycles per CTA (counter 0..3):\n", p.W);
+    for (int r = 0; r < 7; ++r) {
+      double m[4] = {0, 0, 0, 0};
+      for (uint32_t b = 0; b < p.W; ++b)
+        for (int i = 0; i < 4; ++i) m[i] += (double)h[(size_t)b * 64 + r * 4 + i] / p.W;
+      fprintf(stderr, "  %-9s %10.0f %10.0f %10.0f %10.0f\n", role[r], m[0], m[1], m[2], m[3]);
+    }
+  }
   return MSDR_OK;
 }
 
@@ -643,14 +794,15 @@ int msdr_op_fir_demod_tc(int device, uint16_t numTaps, const int16_t *cI, const 
   tc_build_bmat(A.data(), B.data(), C.data(), D.data(), KP, K, bm.data());
   std::vector<uint8_t> hk(rows, (uint8_t)kind0), hs(rows, 0);
   if (kinds) memcpy(hk.data(), kinds, rows);
-  DevBuf din, dout, dbm, dk, ds;
+  DevBuf din, dout, dbm, dk, ds, dctr;
+  OPCK(dctr.alloc(sizeof(int)));
   OPCK(din.alloc(rows * dstride * 2)); OPCK(dout.alloc((size_t)rows * n * 2)); OPCK(dbm.alloc(bm.size())); OPCK(dk.alloc(rows)); OPCK(ds.alloc(rows));
   OPCK(cudaMemset(din.p, 0, rows * dstride * 2));
   OPCK(cudaMemcpy2D(din.as<int16_t>() + pad, dstride * 2, in, stride * 2, (size_t)n * 2, rows, cudaMemcpyHostToDevice));
   OPCK(cudaMemcpy(dbm.p, bm.data(), bm.size(), cudaMemcpyHostToDevice));
   OPCK(cudaMemcpy(dk.p, hk.data(), rows, cudaMemcpyHostToDevice));
   OPCK(cudaMemcpy(ds.p, hs.data(), rows, cudaMemcpyHostToDevice));
-  OPCK(launch_fir_demod_tc(din.as<int16_t>() + pad, dstride, dout.as<int16_t>(), n, rows, n, K, dbm.as<uint8_t>(), ds.as<uint8_t>(), dk.as<uint8_t>(), nullptr));
+  OPCK(launch_fir_demod_tc(din.as<int16_t>() + pad, dstride, dout.as<int16_t>(), n, rows, n, K, dbm.as<uint8_t>(), ds.as<uint8_t>(), dk.as<uint8_t>(), dctr.as<int>(), nullptr));
   OPCK(cudaDeviceSynchronize());
   OPCK(cudaMemcpy2D(out, stride * 2, dout.p, (size_t)n * 2, (size_t)n * 2, rows, cudaMemcpyDeviceToHost));
   return MSDR_OK;
@@ -673,7 +825,8 @@ int msdr_study_fir_demod_tc_time(int device, uint16_t numTaps, uint32_t rows, ui
   tc_build_bmat(A.data(), B.data(), C.data(), D.data(), KP, K, bm.data());
   std::vector<int16_t> hrow(dstride);
   for (size_t i = 0; i < dstride; ++i) { lcg = lcg * 1664525u + 1013904223u; hrow[i] = (int16_t)(lcg >> 16); }
-  DevBuf din, dout, dbm, dk, ds;
+  DevBuf din, dout, dbm, dk, ds, dctr;
+  OPCK(dctr.alloc(sizeof(int)));
   OPCK(din.alloc(rows * dstride * 2)); OPCK(dout.alloc((size_t)rows * n * 2)); OPCK(dbm.alloc(bm.size())); OPCK(dk.alloc(rows)); OPCK(ds.alloc(rows));
   { // the same row pattern everywhere is fine for timing (no data-dependent work): upload 64 rows, replicate on the device
     const uint32_t rep = std::min<uint32_t>(64, rows);
@@ -689,11 +842,11 @@ int msdr_study_fir_demod_tc_time(int device, uint16_t numTaps, uint32_t rows, ui
   cudaEvent_t e0, e1;
   OPCK(cudaEventCreate(&e0)); OPCK(cudaEventCreate(&e1));
   for (int w = 0; w < 3; ++w)
-    OPCK(launch_fir_demod_tc(din.as<int16_t>() + pad, dstride, dout.as<int16_t>(), n, rows, n, K, dbm.as<uint8_t>(), ds.as<uint8_t>(), dk.as<uint8_t>(), nullptr));
+    OPCK(launch_fir_demod_tc(din.as<int16_t>() + pad, dstride, dout.as<int16_t>(), n, rows, n, K, dbm.as<uint8_t>(), ds.as<uint8_t>(), dk.as<uint8_t>(), dctr.as<int>(), nullptr));
   OPCK(cudaDeviceSynchronize());
   OPCK(cudaEventRecord(e0, nullptr));
   for (int it = 0; it < iters; ++it)
-    OPCK(launch_fir_demod_tc(din.as<int16_t>() + pad, dstride, dout.as<int16_t>(), n, rows, n, K, dbm.as<uint8_t>(), ds.as<uint8_t>(), dk.as<uint8_t>(), nullptr));
+    OPCK(launch_fir_demod_tc(din.as<int16_t>() + pad, dstride, dout.as<int16_t>(), n, rows, n, K, dbm.as<uint8_t>(), ds.as<uint8_t>(), dk.as<uint8_t>(), dctr.as<int>(), nullptr));
   OPCK(cudaEventRecord(e1, nullptr));
   OPCK(cudaEventSynchronize(e1));
   float ms = 0.f;

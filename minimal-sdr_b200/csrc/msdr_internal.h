@@ -43,6 +43,15 @@ struct ChainParams {
   uint32_t ablate;        // study only: bit 0 skip the FIR arithmetic, bit 1 skip the biquad arithmetic (results are wrong)
   uint32_t sets_in_smem;  // 0: the tap tables do not fit next to the tile buffers and are read from global memory
   uint32_t am_q31;
+  // tensor-core FIR plan (chain kernel v4, msdr_chain_v4.cu)
+  const uint32_t *tc_rowmap;   // [n_rb][128] launch-relative row, 0xFFFFFFFF = padding
+  const uint4 *tc_rb;          // [n_rb] {table id, first group entry, group entries, wave}
+  const uint32_t *tc_grp;      // group entries: group | rows << 24
+  const uint32_t *tc_wave_rb0; // [n_waves + 1] first row block of each wave
+  const uint8_t *tc_bmat;      // [n_sets][4 * 64 * K] Toeplitz operands
+  uint32_t tc_K, tc_ring, tc_sub;
+  long long *prof;             // developer profile buffer [grid][64] or NULL
+  int *tile_cnt;               // [NG][NT] rows of group g whose span i is in `out` (zeroed before the launch)
 };
 
 struct ChainLaunchInfo {
@@ -55,6 +64,9 @@ struct ChainLaunchInfo {
 cudaError_t launch_chain(const ChainParams &p, cudaStream_t stream, int variant, ChainLaunchInfo *info);
 cudaError_t launch_chain_v3(const ChainParams &p, cudaStream_t stream, int variant, ChainLaunchInfo *info);
 uint32_t chain_tile_samples();
+cudaError_t launch_chain_v4(const ChainParams &p, cudaStream_t stream, int variant, ChainLaunchInfo *info);
+uint32_t chain_v4_span_samples();
+bool chain_v4_config(uint32_t K, int smem_max, uint32_t *ring_out);
 
 // stage-level kernels on device buffers
 cudaError_t launch_mix_fs4(const int16_t *in, int16_t *I, int16_t *Q, uint32_t rows, uint32_t n, size_t stride, cudaStream_t s);
@@ -66,11 +78,12 @@ cudaError_t launch_freq_conv(int dir, int16_t *I, int16_t *Q, const int16_t *osc
                              cudaStream_t s);
 // K3 study: tensor-core FIR + demod (msdr_fir_tc.cu)
 uint32_t tc_window_words(uint32_t T);
+uint32_t tc_window_words_kp(uint32_t KP);
 uint32_t tc_tile_samples();
 uint32_t tc_tile_rows();
 void tc_build_bmat(const int *cA, const int *cB, const int *cC, const int *cD, uint32_t KP, uint32_t K, uint8_t *out);
 cudaError_t launch_fir_demod_tc(const int16_t *in, size_t stride, int16_t *out, size_t ostride, uint32_t rows, uint32_t L, uint32_t K, const uint8_t *bmat,
-                                const uint8_t *row_set, const uint8_t *row_kind, cudaStream_t s);
+                                const uint8_t *row_set, const uint8_t *row_kind, int *counter, cudaStream_t s);
 cudaError_t launch_sqrt_q31(const int32_t *in, int32_t *out, int32_t *status, uint32_t n, cudaStream_t s);
 cudaError_t launch_bq_setcoef(int32_t *bq, uint32_t Cpad, int object, uint32_t ch0, uint32_t nch, uint32_t stage, const int32_t coef[5], cudaStream_t s);
 
