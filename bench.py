@@ -195,7 +195,8 @@ def workload_config(args):
             "channels_per_gpu": args.channels, "blocks_per_channel": nb, "blocks_per_update": args.blocks_per_update,
             "fs_hz": FS, "modes": "{AM,USB,LSB,CW}[c mod 4]", "fir": "sketch tables: AM 102 taps (bw 2800 @ 24 kHz design, used as-is), SSB/CW 86 taps",
             "biquads": "biquad1 low-pass (0.9*IF, Q 0.54) + biquad2 notch (fs/8, Q 15), integer Q2.30",
-            "l2": "inputs (3.6 GB per step) and outputs far exceed the 126 MB L2; no explicit flush", "sharding": "independent channel shards per GPU"}
+            "l2": "inputs (3.6 GB per step) and outputs far exceed the 126 MB L2; no explicit flush", "sharding": "independent channel shards per GPU",
+            "layout": getattr(args, "layout", "updates")}
 
 
 def main():
@@ -210,6 +211,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--layout", choices=["updates", "rows"], default="updates",
+                    help="device-resident input layout: 'updates' = one contiguous [channels][samples] batch per update (how a streaming "
+                         "receiver holds its block batches), 'rows' = one 10 s row per channel, updates are column windows of it")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -246,18 +250,26 @@ def main():
     g.set_option("variant", args.variant)
     configure_chain(g, m, C, ch0)
     x = m.synth.torch_batch(C, L, dev, FS, ch0=ch0)
-    y = torch.empty_like(x)
+    y = torch.empty_like(x) if args.layout == "rows" else None
     torch.cuda.synchronize()
     stream = torch.cuda.Stream(device=dev)  # a real (non-NULL) stream: kernels and timing events share it
     assert stream.cuda_stream != 0
     g.set_stream(stream.cuda_stream)
-    stride = x.stride(0)
-
     updates = [(b0, min(bpu, nb_total - b0)) for b0 in range(0, nb_total, bpu)]
+    if args.layout == "rows":
+        stride = x.stride(0)
+        calls = [(x.data_ptr() + 2 * b0 * BLOCK, y.data_ptr() + 2 * b0 * BLOCK, nb, stride) for b0, nb in updates]
+    else:  # one contiguous batch per update; same samples, same order of processing
+        xs = [x[:, b0 * BLOCK:(b0 + nb) * BLOCK].contiguous() for b0, nb in updates]
+        ys = [torch.empty_like(t) for t in xs]
+        calls = [(xi.data_ptr(), yi.data_ptr(), nb, xi.stride(0)) for (b0, nb), xi, yi in zip(updates, xs, ys)]
+        if args.e2e_steps <= 0:
+            del x
+        torch.cuda.empty_cache()
 
     def step():
-        for b0, nb in updates:
-            g.update_device(x.data_ptr() + 2 * b0 * BLOCK, y.data_ptr() + 2 * b0 * BLOCK, nb, stride)
+        for d_in, d_out, nb, stride in calls:
+            g.update_device(d_in, d_out, nb, stride)
 
     def barrier():
         if world > 1:

@@ -166,6 +166,9 @@ int msdr_op_fir_demod_tc(int device, uint16_t numTaps, const int16_t *cI, const 
                          int16_t *out, uint32_t rows, uint32_t n, size_t stride);
 /* Device-resident timing of the same kernel on pseudo-random data: milliseconds per launch over `iters` launches. */
 int msdr_study_fir_demod_tc_time(int device, uint16_t numTaps, uint32_t rows, uint32_t n, int kind0, int iters, float *ms_per_iter);
+/* Exhaustive device check: the epilogue's branch-free float square root against sqrt.rn.f32 for every AM envelope argument
+ * (integers 0 .. 2^31-1, arm_sqrt_f32 of Minimal-SDR.ino:606); *mismatches must come back 0. */
+int msdr_study_sqrt_check(int device, uint64_t *mismatches);
 
 const char *msdr_version(void);
 

@@ -65,6 +65,7 @@ SYMBOLS = {
     "msdr_op_sqrt_q31": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
     "msdr_op_fir_demod_tc": (C.c_int, [C.c_int, C.c_uint16, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_size_t]),
     "msdr_study_fir_demod_tc_time": (C.c_int, [C.c_int, C.c_uint16, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "msdr_study_sqrt_check": (C.c_int, [C.c_int, C.POINTER(C.c_uint64)]),
     "msdr_version": (C.c_char_p, []),
 }
 

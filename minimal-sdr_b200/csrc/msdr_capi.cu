@@ -497,7 +497,8 @@ int msdr_chain_update_range_device(msdr_chain *chain, uint32_t ch0, uint32_t nch
       p.n_items = pl.n_rb * p.NT;
       p.tc_rowmap = pl.d_rowmap; p.tc_rb = pl.d_rb; p.tc_grp = pl.d_grp; p.tc_wave_rb0 = pl.d_wave_rb0; p.tc_bmat = pl.d_bmat;
       p.tc_K = pl.K; p.tc_ring = pl.ring;
-      const size_t n_cnt = (size_t)NG * p.NT;
+      p.NU = p.L / chain_v4_unit_samples();
+      const size_t n_cnt = (size_t)NG * p.NU;
       if (n_cnt > chain->tile_cnt_len) {
         CK(cudaStreamSynchronize(chain->stream));
         cudaFree(chain->d_tile_cnt);
@@ -805,6 +806,22 @@ int msdr_op_fir_demod_tc(int device, uint16_t numTaps, const int16_t *cI, const 
   OPCK(launch_fir_demod_tc(din.as<int16_t>() + pad, dstride, dout.as<int16_t>(), n, rows, n, K, dbm.as<uint8_t>(), ds.as<uint8_t>(), dk.as<uint8_t>(), dctr.as<int>(), nullptr));
   OPCK(cudaDeviceSynchronize());
   OPCK(cudaMemcpy2D(out, stride * 2, dout.p, (size_t)n * 2, (size_t)n * 2, rows, cudaMemcpyDeviceToHost));
+  return MSDR_OK;
+}
+
+// Study check: the branch-free float square root of the tensor-core epilogue equals __fsqrt_rn for every envelope argument.
+int msdr_study_sqrt_check(int device, uint64_t *mismatches)
+{
+  if (!mismatches) return MSDR_ERR_ARGUMENT;
+  int st = op_begin(device); if (st) return st;
+  DevBuf d;
+  OPCK(d.alloc(8));
+  OPCK(cudaMemset(d.p, 0, 8));
+  OPCK(launch_sqrt_check(d.as<unsigned long long>(), nullptr));
+  OPCK(cudaDeviceSynchronize());
+  unsigned long long h = 0;
+  OPCK(cudaMemcpy(&h, d.p, 8, cudaMemcpyDeviceToHost));
+  *mismatches = h;
   return MSDR_OK;
 }
 

@@ -32,7 +32,8 @@ namespace v4 {
 
 using namespace tc;
 
-constexpr int SPAN = 512;          // samples per FIR work item and per readiness counter
+constexpr int SPAN = 512;          // samples per FIR work item
+constexpr int UNIT = 128;          // samples per readiness counter: a chain starts on a span after its first two tiles
 // chain sub-tile ring: one slot being filtered by warp A, one by warp B, one draining to `out`, two landing.  With fewer
 // slots the load of a sub-tile can only be issued when it is already needed and its latency (~2 k cycles) is paid per sub-tile.
 constexpr int NSLOT = 5;
@@ -254,14 +255,15 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
             if (orow_g != 0xFFFFFFFFu)
               *reinterpret_cast<uint4 *>(p.out + (size_t)orow_g * p.stride + (size_t)t * N + c * 8) = *reinterpret_cast<const uint4 *>(sOut + r * OW + c * 4);
           }
+          if ((((t + 1) * N) % UNIT) == 0) { // publish: every row of this block has the unit in `out`
+            __threadfence();
+            named_bar_sync(2, 128);
+            if ((uint32_t)tid < rbi.z) {
+              const uint32_t e = __ldg(p.tc_grp + rbi.y + tid);
+              atomicAdd(p.tile_cnt + (size_t)(e & 0xFFFFFFu) * p.NU + (t * N) / UNIT, (int)(e >> 24));
+            }
+          }
           prof.lap(2);
-        }
-        // publish: every row of this block has its span in `out`
-        __threadfence();
-        named_bar_sync(2, 128);
-        if ((uint32_t)tid < rbi.z) {
-          const uint32_t e = __ldg(p.tc_grp + rbi.y + tid);
-          atomicAdd(p.tile_cnt + (size_t)(e & 0xFFFFFFu) * p.NT + span, (int)(e >> 24));
         }
       }
     }
@@ -327,38 +329,40 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
     prof.flush();
   } else if (warp == kLoadWarp || warp == kStoreWarp) {
     // ================================================================== chain I/O: sub-tiles `out` -> smem ring -> `out`
-    // Plain coalesced 16-byte accesses by two dedicated warps: 32 rows x 256 B per sub-tile are 16 instructions per lane, while
-    // 32 per-row bulk copies per direction kept the SM's copy engine busier than the biquad itself.
+    // Plain coalesced 16-byte accesses by two dedicated warps (32 per-row bulk copies per direction kept the SM's copy engine
+    // busier than the biquad itself).  A warp instruction covers 32 >> lg rows of 1 << lg chunks; all addresses advance by
+    // constants, so a sub-tile costs 32 << lg >> 5 loads and stores per lane and little else.
     const bool isLoad = (warp == kLoadWarp);
     const int SUB = (int)p.tc_sub, BW = SUB / 2 + 4;
     const uint32_t kSlotBytes = slot_bytes(p.tc_sub);
-    const int nsub = (int)((p.L + SUB - 1) / SUB);
+    const int nsub = (int)((p.L + SUB - 1) / SUB); // L is a multiple of 128 and SUB is 64 or 128: sub-tiles are always full
     Prof prof(p.prof, isLoad ? 5 : 6);
-    const int lg = SUB == 128 ? 4 : 3;
+    const int lg = SUB == 128 ? 4 : 3;           // log2 of the 16-byte chunks per row
+    const int rpi = 32 >> lg, nins = kGroup / rpi; // rows per warp instruction, instructions per sub-tile
+    const int r0 = lane >> lg, c = lane & ((1 << lg) - 1);
+    const size_t gstep = (size_t)rpi * p.stride * 2u;  // bytes between the rows of consecutive instructions
+    const uint32_t sstep = (uint32_t)rpi * BW * 4u;
     uint32_t pos = 0;
     for (int g = (int)blockIdx.x; g < (int)p.NG; g += (int)p.W) {
       const int nrows = min(kGroup, (int)p.C - g * kGroup);
-      int16_t *gbase = p.out + (size_t)g * kGroup * p.stride;
-      int ready = 0; // leading spans known to be in `out` for every row of the group
+      unsigned char *gp0 = reinterpret_cast<unsigned char *>(p.out + ((size_t)g * kGroup + r0) * p.stride) + c * 16;
+      int ready = 0; // leading units known to be in `out` for every row of the group
       for (int k = 0; k < nsub; ++k, ++pos) {
         const int slot = (int)(pos % NSLOT);
         const uint32_t phs = (pos / NSLOT) & 1u;
-        uint32_t *sb = reinterpret_cast<uint32_t *>(bq_base + (uint32_t)slot * kSlotBytes);
-        // L is a multiple of 128 and SUB is 64 or 128: sub-tiles are always full, 16-byte chunks per row = 1 << lg
-        const int total = nrows << lg;
+        unsigned char *sp0 = bq_base + (uint32_t)slot * kSlotBytes + (uint32_t)r0 * BW * 4u + c * 16;
+        unsigned char *gp = gp0 + (size_t)k * SUB * 2u;
         if (isLoad) {
           prof.start();
-          const int need = (k * SUB) / SPAN;
-          while (ready <= need) { // all rows of the group have this span in `out`
-            int ok = 0;
+          const int need = (k * SUB) / UNIT;
+          while (ready <= need) { // all rows of the group have this unit in `out`
             if (lane == 0) {
               const long long t0 = clock64();
-              for (;;) {
-                ok = ld_acquire_gpu(p.tile_cnt + (size_t)g * p.NT + ready) >= nrows;
-                if (ok) break;
-                __nanosleep(100);
+              while (ld_relaxed_gpu(p.tile_cnt + (size_t)g * p.NU + ready) < nrows) {
+                __nanosleep(64);
                 if (clock64() - t0 > kWatchdogCycles) __trap();
               }
+              fence_acquire_gpu();
             }
             __syncwarp();
             ++ready;
@@ -366,41 +370,29 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
           prof.lap(0);
           mbar_wait(&pc->slot_free[slot], phs ^ 1u);
           prof.lap(1);
-          for (int i0 = 0; i0 < total; i0 += 32 * 8) {
+          // weak loads: the acquire fence above ordered them after the producers' stores (and dropped this SM's L1 lines)
+          for (int i0 = 0; i0 < nins; i0 += 8) {
             uint4 v[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int i = i0 + j * 32 + lane;
-              if (i < total) {
-                const int r = i >> lg, c = i & ((1 << lg) - 1);
-                v[j] = __ldcg(reinterpret_cast<const uint4 *>(gbase + (size_t)r * p.stride + (size_t)k * SUB) + c);
-              }
-            }
+            for (int j = 0; j < 8; ++j)
+              if (r0 + (i0 + j) * rpi < nrows) v[j] = *reinterpret_cast<const uint4 *>(gp + (size_t)(i0 + j) * gstep);
+            prof.lap(2);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int i = i0 + j * 32 + lane;
-              if (i < total) {
-                const int r = i >> lg, c = i & ((1 << lg) - 1);
-                *reinterpret_cast<uint4 *>(sb + (uint32_t)r * BW + c * 4) = v[j];
-              }
-            }
+            for (int j = 0; j < 8; ++j)
+              if (r0 + (i0 + j) * rpi < nrows) *reinterpret_cast<uint4 *>(sp0 + (uint32_t)(i0 + j) * sstep) = v[j];
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(&pc->ld_full[slot]);
-          prof.lap(2);
+          prof.lap(3);
         } else {
           prof.start();
           mbar_wait(&pc->st_full[slot], phs);
           prof.lap(0);
-          for (int i0 = 0; i0 < total; i0 += 32 * 8) {
+          for (int i0 = 0; i0 < nins; i0 += 8) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int i = i0 + j * 32 + lane;
-              if (i < total) {
-                const int r = i >> lg, c = i & ((1 << lg) - 1);
-                *(reinterpret_cast<uint4 *>(gbase + (size_t)r * p.stride + (size_t)k * SUB) + c) = *reinterpret_cast<const uint4 *>(sb + (uint32_t)r * BW + c * 4);
-              }
-            }
+            for (int j = 0; j < 8; ++j)
+              if (r0 + (i0 + j) * rpi < nrows)
+                *reinterpret_cast<uint4 *>(gp + (size_t)(i0 + j) * gstep) = *reinterpret_cast<const uint4 *>(sp0 + (uint32_t)(i0 + j) * sstep);
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(&pc->slot_free[slot]);
@@ -439,6 +431,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
 } // namespace v4
 
 uint32_t chain_v4_span_samples() { return v4::SPAN; }
+uint32_t chain_v4_unit_samples() { return v4::UNIT; }
 
 // largest window the fused kernel can hold next to its other buffers; 0 = the tensor-core form does not apply
 bool chain_v4_config(uint32_t K, int smem_max, uint32_t *ring_out)

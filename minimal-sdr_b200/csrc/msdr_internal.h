@@ -50,8 +50,9 @@ struct ChainParams {
   const uint32_t *tc_wave_rb0; // [n_waves + 1] first row block of each wave
   const uint8_t *tc_bmat;      // [n_sets][4 * 64 * K] Toeplitz operands
   uint32_t tc_K, tc_ring, tc_sub;
+  uint32_t NU;                 // readiness units per channel (v4)
   long long *prof;             // developer profile buffer [grid][64] or NULL
-  int *tile_cnt;               // [NG][NT] rows of group g whose span i is in `out` (zeroed before the launch)
+  int *tile_cnt;               // [NG][NU] rows of group g whose unit u is in `out` (zeroed before the launch)
 };
 
 struct ChainLaunchInfo {
@@ -66,6 +67,7 @@ cudaError_t launch_chain_v3(const ChainParams &p, cudaStream_t stream, int varia
 uint32_t chain_tile_samples();
 cudaError_t launch_chain_v4(const ChainParams &p, cudaStream_t stream, int variant, ChainLaunchInfo *info);
 uint32_t chain_v4_span_samples();
+uint32_t chain_v4_unit_samples();
 bool chain_v4_config(uint32_t K, int smem_max, uint32_t *ring_out);
 
 // stage-level kernels on device buffers
@@ -84,6 +86,7 @@ uint32_t tc_tile_rows();
 void tc_build_bmat(const int *cA, const int *cB, const int *cC, const int *cD, uint32_t KP, uint32_t K, uint8_t *out);
 cudaError_t launch_fir_demod_tc(const int16_t *in, size_t stride, int16_t *out, size_t ostride, uint32_t rows, uint32_t L, uint32_t K, const uint8_t *bmat,
                                 const uint8_t *row_set, const uint8_t *row_kind, int *counter, cudaStream_t s);
+cudaError_t launch_sqrt_check(unsigned long long *d_mismatch, cudaStream_t s);
 cudaError_t launch_sqrt_q31(const int32_t *in, int32_t *out, int32_t *status, uint32_t n, cudaStream_t s);
 cudaError_t launch_bq_setcoef(int32_t *bq, uint32_t Cpad, int object, uint32_t ch0, uint32_t nch, uint32_t stage, const int32_t coef[5], cudaStream_t s);
 

@@ -246,4 +246,21 @@ cudaError_t launch_bq_setcoef(int32_t *bq, uint32_t Cpad, int object, uint32_t c
   return cudaGetLastError();
 }
 
+
+// exhaustive check of sqrt_rn_fast against __fsqrt_rn over the envelope's argument domain s in [0, 2^31)
+__global__ void sqrt_check_kernel(unsigned long long *mismatch)
+{
+  unsigned long long bad = 0;
+  for (unsigned long long s = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; s < 0x80000000ull; s += (unsigned long long)gridDim.x * blockDim.x) {
+    const float f = __int2float_rn((int)s);
+    if (__float_as_int(sqrt_rn_fast(f)) != __float_as_int(__fsqrt_rn(f))) ++bad;
+  }
+  if (bad) atomicAdd(mismatch, bad);
+}
+cudaError_t launch_sqrt_check(unsigned long long *d_mismatch, cudaStream_t s)
+{
+  sqrt_check_kernel<<<148 * 16, 256, 0, s>>>(d_mismatch);
+  return cudaGetLastError();
+}
+
 } // namespace msdr

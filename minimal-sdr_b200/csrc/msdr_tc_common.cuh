@@ -80,6 +80,17 @@ __device__ __forceinline__ void issue_init(IssueCtx &c, const uint8_t *sA, uint3
     c.descB[i] = make_desc(smem_u32(sB + i * b_plane), kKStrideB, 128);
   }
 }
+// Accumulators per branch: 0 = hi*hi, 1 = hi*lo + lo*hi (two MMAs into the same accumulator), 2 = lo*lo.
+constexpr int kAccPerBranch = 3;
+__device__ __forceinline__ void umma_i8(uint32_t dcol, uint64_t da, uint64_t db, uint32_t a_signed, uint32_t b_signed, uint32_t acc)
+{
+  const uint32_t idesc = (2u << 4) | (a_signed << 7) | (b_signed << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+      ::"r"(dcol), "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(0), "r"(0), "r"(0), "r"(0)
+      : "memory");
+}
 __device__ __forceinline__ void issue_tile(const IssueCtx &c, uint32_t tmem, uint32_t qt, uint32_t KS, uint32_t ring)
 {
   uint32_t pos = (qt - (KS - 1)) % ring;
@@ -88,32 +99,33 @@ __device__ __forceinline__ void issue_tile(const IssueCtx &c, uint32_t tmem, uin
     const uint32_t acc = ks > 0;
 #pragma unroll
     for (uint32_t br = 0; br < 2; ++br) {
-#pragma unroll
-      for (uint32_t combo = 0; combo < 4; ++combo) {
-        const uint32_t ah = combo >> 1, bh = combo & 1; // 0 = hi plane (signed), 1 = lo plane (unsigned)
-        const uint32_t idesc = (2u << 4) | ((ah == 0 ? 1u : 0u) << 7) | ((bh == 0 ? 1u : 0u) << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-        const uint64_t da = c.descA[2 * br + ah] + aoff, db = c.descB[2 * br + bh] + boff;
-        const uint32_t dcol = tmem + (br * 4 + combo) * N;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
-            ::"r"(dcol), "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(0), "r"(0), "r"(0), "r"(0)
-            : "memory");
-      }
+      const uint64_t a_hi = c.descA[2 * br] + aoff, a_lo = c.descA[2 * br + 1] + aoff; // hi planes are signed bytes, lo planes unsigned
+      const uint64_t b_hi = c.descB[2 * br] + boff, b_lo = c.descB[2 * br + 1] + boff;
+      const uint32_t d0 = tmem + (br * kAccPerBranch) * N;
+      umma_i8(d0, a_hi, b_hi, 1, 1, acc);
+      umma_i8(d0 + N, a_hi, b_lo, 1, 0, acc);
+      umma_i8(d0 + N, a_lo, b_hi, 0, 1, 1);
+      umma_i8(d0 + 2 * N, a_lo, b_lo, 0, 0, acc);
     }
     pos = pos + 1 == ring ? 0 : pos + 1;
   }
 }
 
 // Epilogue step 1 (thread = TMEM lane = channel row): accumulators -> recombine -> >>15 -> SSAT16 (arm_fir_fast_q15.c:234-238)
-// -> packed (I | Q << 16) parked in this thread's staging row.
+// -> packed (I | Q << 16) parked in this thread's staging row.  cvt.pack.sat saturates and packs both branches at once.
+__device__ __forceinline__ uint32_t pack_sat_iq(int I, int Q)
+{
+  uint32_t d;
+  asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(d) : "r"(Q), "r"(I)); // upper half <- sat16(Q), lower half <- sat16(I)
+  return d;
+}
 __device__ __forceinline__ void drain_tile(uint32_t lane_addr, uint32_t *orow)
 {
 #pragma unroll
   for (int c0 = 0; c0 < N; c0 += 8) {
-    uint32_t acc[8][8]; // [branch*4 + combo][column]
+    uint32_t acc[2 * kAccPerBranch][8]; // [branch*3 + part][column]
 #pragma unroll
-    for (int a = 0; a < 8; ++a) {
+    for (int a = 0; a < 2 * kAccPerBranch; ++a) {
       asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                    : "=r"(acc[a][0]), "=r"(acc[a][1]), "=r"(acc[a][2]), "=r"(acc[a][3]), "=r"(acc[a][4]), "=r"(acc[a][5]), "=r"(acc[a][6]), "=r"(acc[a][7])
                    : "r"(lane_addr + (uint32_t)(a * N + c0)));
@@ -122,11 +134,9 @@ __device__ __forceinline__ void drain_tile(uint32_t lane_addr, uint32_t *orow)
     uint32_t iq[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      // combos: 0 = hi*hi, 1 = hi(x)*lo(c), 2 = lo(x)*hi(c), 3 = lo*lo
-      const uint32_t ai = (acc[0][j] << 16) + ((acc[1][j] + acc[2][j]) << 8) + acc[3][j];
-      const uint32_t aq = (acc[4][j] << 16) + ((acc[5][j] + acc[6][j]) << 8) + acc[7][j];
-      const int I = ssat16((int)ai >> 15), Q = ssat16((int)aq >> 15);
-      iq[j] = ((uint32_t)I & 0xFFFFu) | ((uint32_t)Q << 16);
+      const uint32_t ai = (acc[0][j] << 16) + (acc[1][j] << 8) + acc[2][j]; // mod 2^32, like the reference accumulator
+      const uint32_t aq = (acc[3][j] << 16) + (acc[4][j] << 8) + acc[5][j];
+      iq[j] = pack_sat_iq((int)ai >> 15, (int)aq >> 15);
     }
     *reinterpret_cast<uint4 *>(orow + c0) = make_uint4(iq[0], iq[1], iq[2], iq[3]);
     *reinterpret_cast<uint4 *>(orow + c0 + 4) = make_uint4(iq[4], iq[5], iq[6], iq[7]);
@@ -143,7 +153,7 @@ __device__ __forceinline__ int demod_inline(int I, int Q, int sgn)
   const int s = (int)((uint32_t)(I * I) + (uint32_t)(Q * Q));
   if (KIND == 2) {
     const float f = __int2float_rn(s);
-    const float r = (f >= 0.0f) ? __fsqrt_rn(f) : 0.0f; // arm_sqrt_f32, arm_math.h:5733-5760
+    const float r = (f >= 0.0f) ? sqrt_rn_fast(f) : 0.0f; // arm_sqrt_f32, arm_math.h:5733-5760
     return (int)(short)__float2int_rz(r);
   }
   return (int)(short)(sqrt_q31(s, nullptr) >> 16);

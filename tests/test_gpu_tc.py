@@ -70,3 +70,12 @@ def test_tc_is_tensor_core_code(msdr):
         pytest.skip("cuobjdump not available")
     sass = subprocess.run(["cuobjdump", "-sass", msdr.lib_path()], capture_output=True, text=True).stdout
     assert "UTCIMMA" in sass and "LDTM" in sass
+
+
+def test_tc_envelope_sqrt_equals_sqrt_rn_everywhere(msdr):
+    """The epilogue's branch-free sqrtf is bit-identical to sqrt.rn.f32 for EVERY AM envelope argument (2^31 integers)."""
+    import ctypes as C
+    bad = C.c_uint64(123)
+    st = msdr.capi.lib().msdr_study_sqrt_check(0, C.byref(bad))
+    assert st == 0
+    assert bad.value == 0
