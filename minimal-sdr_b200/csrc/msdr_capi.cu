@@ -93,7 +93,7 @@ struct msdr_chain {
   uint64_t meta_version = 1;  // bumped whenever a channel's table binding or a table's contents change
   struct TcPlan {
     uint64_t version = 0;
-    uint32_t ch0 = 0, nch = 0, W = 0, K = 0, ring = 0, n_rb = 0, n_waves = 0;
+    uint32_t ch0 = 0, nch = 0, W = 0, K = 0, rings[3] = {0, 0, 0}, n_rb = 0, n_waves = 0;
     bool usable = false;
     uint32_t *d_rowmap = nullptr, *d_grp = nullptr, *d_wave_rb0 = nullptr;
     uint4 *d_rb = nullptr;
@@ -389,9 +389,8 @@ int build_tc_plan(msdr_chain *chain, uint32_t ch0, uint32_t nch, uint32_t W)
   const uint32_t K = tc_window_words_kp(kp_max);
   int smem_max = 0;
   CK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, chain->device));
-  uint32_t ring = 0;
-  if (!chain_v4_config(K, smem_max, &ring)) { pl.usable = false; return MSDR_OK; }
-  pl.K = K; pl.ring = ring;
+  if (!chain_v4_config(K, smem_max, pl.rings)) { pl.usable = false; return MSDR_OK; }
+  pl.K = K;
 
   const uint32_t NG = (nch + kGroup - 1) / kGroup, n_sets = (uint32_t)chain->sets.size(), M = tc_tile_rows();
   std::vector<uint32_t> rowmap, grp, wave_rb0;
@@ -496,7 +495,12 @@ int msdr_chain_update_range_device(msdr_chain *chain, uint32_t ch0, uint32_t nch
       p.W = (uint32_t)sms;
       p.n_items = pl.n_rb * p.NT;
       p.tc_rowmap = pl.d_rowmap; p.tc_rb = pl.d_rb; p.tc_grp = pl.d_grp; p.tc_wave_rb0 = pl.d_wave_rb0; p.tc_bmat = pl.d_bmat;
-      p.tc_K = pl.K; p.tc_ring = pl.ring;
+      // kernel shape: post warps where they fit, else the plain classic shape; variant bit 7 asks for the FF chain side and
+      // bit 8 for the classic shape without post warps (study knobs)
+      uint32_t shape = pl.rings[0] ? 0u : 1u;
+      if ((chain->variant & 256) && pl.rings[1]) shape = 1u;
+      if ((chain->variant & 128) && pl.rings[2]) shape = 2u;
+      p.tc_K = pl.K; p.tc_ring = pl.rings[shape]; p.tc_ff = shape;
       p.NU = p.L / chain_v4_unit_samples();
       const size_t n_cnt = (size_t)NG * p.NU;
       if (n_cnt > chain->tile_cnt_len) {
@@ -527,9 +531,9 @@ int msdr_chain_update_range_device(msdr_chain *chain, uint32_t ch0, uint32_t nch
     CK(cudaMemcpyAsync(h.data(), d_prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, chain->stream));
     CK(cudaStreamSynchronize(chain->stream));
     cudaFree(d_prof);
-    static const char *role[7] = {"convert", "mma", "epilogue", "chainA", "chainB", "load", "store"};
+    static const char *role[8] = {"convert", "mma", "epilogue", "chainA", "chainB", "load", "store", "ff2/post"};
     fprintf(stderr, "[msdr prof] grid %u, mean cycles per CTA (counter 0..3):\n", p.W);
-    for (int r = 0; r < 7; ++r) {
+    for (int r = 0; r < 8; ++r) {
       double m[4] = {0, 0, 0, 0};
       for (uint32_t b = 0; b < p.W; ++b)
         for (int i = 0; i < 4; ++i) m[i] += (double)h[(size_t)b * 64 + r * 4 + i] / p.W;

@@ -199,4 +199,75 @@ __device__ __forceinline__ void bq_store_stage(const BqStageD &s, uint32_t flag,
   b[7 * (size_t)Cpad] = (int32_t)((uint32_t)s.res | flag);
 }
 
+
+// ---- one stage split in two (chain kernel v4, FF shape) ---------------------------------------------------------------
+// filter_biquad.cpp:56-63 per sample:  sum = res + b0 x[n] + b1 x[n-1] + b2 x[n-2] + a1 y[n-1] + a2 y[n-2]  (SMLAW products,
+// adds wrap mod 2^32, so the order is free).  The three input-side products depend on the input only: a helper warp forms
+//   e[n] = hi(b0 x[n]) + hi(b1 x[n-1]) + hi(b2 x[n-2])
+// for a whole sub-tile, and the chain warp is left with the recurrence  sum = e[n] + res + hi(a2 y[n-2]) + hi(a1 y[n-1]).
+// The helper warps form e[n] on the FP64 pipe (exact DFMA.RM form of msdr_device.cuh): the integer-multiply pipe of their
+// sub-partition stays free for the tensor-core epilogue and the converters that live there.
+struct BqFF {
+  double b0, b1, b2; // coefficient * 2^-16
+  double x1, x2;     // D-form input history
+  int negk;          // -17 * (b0 + b1 + b2)  (mod 2^32)
+};
+struct BqRec {
+  int a1, a2; // already negated as stored by setCoefficients (filter_biquad.cpp:93-94)
+  int y1, y2; // << 16
+  int res;
+};
+// x: the int16 input value, sign-extended
+__device__ __forceinline__ int ff_step(BqFF &f, int x)
+{
+  const double xD = bq_d_from_int(x);
+  const int e = bq_term_d(f.b0, xD) + bq_term_d(f.b1, f.x1) + bq_term_d(f.b2, f.x2) + f.negk;
+  f.x2 = f.x1; f.x1 = xD;
+  return e;
+}
+// returns y << 16
+__device__ __forceinline__ int rec_step(BqRec &r, int e)
+{
+  int pre;
+  asm("mad.hi.s32 %0, %1, %2, %3;" : "=r"(pre) : "r"(r.a2), "r"(r.y2), "r"(e));
+  pre += r.res;
+  const int sum = smlaw_s(pre, r.a1, r.y1);
+  int ys;
+  asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(ys) : "r"(sum >> 14), "r"(0)); // ssat #16, asr #14, << 16
+  r.res = sum & 0x3FFF;
+  r.y2 = r.y1; r.y1 = ys;
+  return ys;
+}
+__device__ __forceinline__ void bq_load_ff(BqFF &f, const int32_t *__restrict__ bq, uint32_t Cpad, int obj, uint32_t ch)
+{
+  const int32_t *b = bq + (size_t)(obj * 4 * 8) * Cpad + ch;
+  const int b0 = __ldcg(b + 0 * (size_t)Cpad), b1 = __ldcg(b + 1 * (size_t)Cpad), b2 = __ldcg(b + 2 * (size_t)Cpad);
+  const double k = 1.0 / 65536.0;
+  f.b0 = (double)b0 * k; f.b1 = (double)b1 * k; f.b2 = (double)b2 * k;
+  f.negk = (int)(0u - 17u * ((uint32_t)b0 + (uint32_t)b1 + (uint32_t)b2));
+  const uint32_t w5 = (uint32_t)__ldcg(b + 5 * (size_t)Cpad); // (x[n-1] << 16) | (x[n-2] & 0xffff), filter_biquad.cpp:66-69
+  f.x1 = bq_d_from_int((int)w5 >> 16);
+  f.x2 = bq_d_from_int((int)(short)(w5 & 0xFFFFu));
+}
+__device__ __forceinline__ void bq_store_ff(const BqFF &f, int32_t *__restrict__ bq, uint32_t Cpad, int obj, uint32_t ch)
+{
+  bq[(size_t)(obj * 4 * 8 + 5) * Cpad + ch] = (int32_t)(((uint32_t)bq_int_from_d(f.x1) << 16) | ((uint32_t)bq_int_from_d(f.x2) & 0xFFFFu));
+}
+__device__ __forceinline__ void bq_load_rec(BqRec &r, uint32_t &flag, const int32_t *__restrict__ bq, uint32_t Cpad, int obj, uint32_t ch)
+{
+  const int32_t *b = bq + (size_t)(obj * 4 * 8) * Cpad + ch;
+  r.a1 = __ldcg(b + 3 * (size_t)Cpad);
+  r.a2 = __ldcg(b + 4 * (size_t)Cpad);
+  bq_unpack_hist((uint32_t)__ldcg(b + 6 * (size_t)Cpad), r.y1, r.y2);
+  const uint32_t w7 = (uint32_t)__ldcg(b + 7 * (size_t)Cpad);
+  r.res = (int)(w7 & 0x3FFFu);
+  flag = w7 & 0x80000000u;
+}
+__device__ __forceinline__ void bq_store_rec(const BqRec &r, uint32_t flag, int32_t *__restrict__ bq, uint32_t Cpad, int obj, uint32_t ch)
+{
+  int32_t *b = bq + (size_t)(obj * 4 * 8) * Cpad + ch;
+  b[6 * (size_t)Cpad] = (int32_t)bq_pack_hist(r.y1, r.y2);
+  b[7 * (size_t)Cpad] = (int32_t)((uint32_t)r.res | flag);
+}
+
 } // namespace msdr

@@ -49,7 +49,7 @@ struct ChainParams {
   const uint32_t *tc_grp;      // group entries: group | rows << 24
   const uint32_t *tc_wave_rb0; // [n_waves + 1] first row block of each wave
   const uint8_t *tc_bmat;      // [n_sets][4 * 64 * K] Toeplitz operands
-  uint32_t tc_K, tc_ring, tc_sub;
+  uint32_t tc_K, tc_ring, tc_sub, tc_ff; // tc_ff: kernel shape 0/1/2 (msdr_chain_v4.cu: chain_v4_config)
   uint32_t NU;                 // readiness units per channel (v4)
   long long *prof;             // developer profile buffer [grid][64] or NULL
   int *tile_cnt;               // [NG][NU] rows of group g whose unit u is in `out` (zeroed before the launch)
@@ -68,7 +68,7 @@ uint32_t chain_tile_samples();
 cudaError_t launch_chain_v4(const ChainParams &p, cudaStream_t stream, int variant, ChainLaunchInfo *info);
 uint32_t chain_v4_span_samples();
 uint32_t chain_v4_unit_samples();
-bool chain_v4_config(uint32_t K, int smem_max, uint32_t *ring_out);
+bool chain_v4_config(uint32_t K, int smem_max, uint32_t rings[3]);
 
 // stage-level kernels on device buffers
 cudaError_t launch_mix_fs4(const int16_t *in, int16_t *I, int16_t *Q, uint32_t rows, uint32_t n, size_t stride, cudaStream_t s);

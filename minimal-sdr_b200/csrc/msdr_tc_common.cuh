@@ -152,9 +152,13 @@ __device__ __forceinline__ int demod_inline(int I, int Q, int sgn)
   if (KIND <= 1) return (int)(short)(I + sgn * Q); // kind 0 (LSB): I - Q, kind 1 (USB): I + Q
   const int s = (int)((uint32_t)(I * I) + (uint32_t)(Q * Q));
   if (KIND == 2) {
-    const float f = __int2float_rn(s);
-    const float r = (f >= 0.0f) ? sqrt_rn_fast(f) : 0.0f; // arm_sqrt_f32, arm_math.h:5733-5760
-    return (int)(short)__float2int_rz(r);
+    // arm_sqrt_f32 (arm_math.h:5733-5760): sqrtf for in >= 0, else 0.  s < 0 only for I = Q = -32768 (s wraps to -2^31).
+    // Computed unconditionally and selected at the end: a branch per sample would serialise the eight square roots in flight.
+    // (the select is an AND with an arithmetic mask: a ?: lets the compiler sink the whole chain back under a branch)
+    const float r = sqrt_rn_fast(__uint2float_rn((uint32_t)s));
+    const int y = __float2int_rz(r);
+    const int positive = ((-s) & ~s) >> 31; // -1 for s > 0, else 0
+    return (int)(short)(y & positive);
   }
   return (int)(short)(sqrt_q31(s, nullptr) >> 16);
 }

@@ -299,3 +299,25 @@ def test_update_range_device(msdr, orc, K):
         g.update_range_device(c0, n, d_in[c0:].data_ptr(), d_out[c0:].data_ptr(), 6, d_in.stride(0))
     g.synchronize()
     assert_same(d_out.cpu().numpy(), yo, "range update")
+
+
+@pytest.mark.parametrize("variant,name", [(0, "tensor-core FIR + post warps"), (256, "tensor-core FIR, inline epilogue"),
+                                            (128, "tensor-core FIR, feed-forward helper warps"), (64, "CUDA-core FIR (v3)"), (65, "v3, FP64 biquad")])
+def test_every_kernel_shape_is_bit_exact(msdr, orc, K, variant, name):
+    """All shapes of the fused kernel (option "variant") produce the oracle's bits: mixed modes, ragged updates, 4-stage cascades on
+    some channels, full-range (wrapping) taps on others, extreme inputs, a partial last group."""
+    rng = np.random.default_rng(variant)
+    modes = msdr.synth.mixed_modes(200) + [SYNCAM, AM, CW]
+    x = msdr.synth.batch(modes, 128 * 41)
+    x[7] = rng.integers(-32768, 32768, x.shape[1], dtype=np.int16)
+    x[8] = -32768
+    lp, notch = K["biquad1_lowpass_coef"], K["biquad2_notch_coef"]
+    bq = [(0, 0, lp, 0, None), (1, 0, notch, 0, None)]
+    bq += [(0, st, lp, 40, 10) for st in range(1, 4)] + [(1, st, lp, 100, 32) for st in range(1, 4)]
+    g, o = configure_pair(msdr, orc, K, modes, biquads=bq)
+    g.set_option("variant", variant)
+    cI, cQ = wrap_coeffs(86, rng), wrap_coeffs(86, rng)  # the accumulator wraps, outputs saturate
+    g.fir_init(cI, cQ, 7, 2)
+    assert o.fir_init(7, 2, cI, cQ) == 0
+    yg, yo = run_pair(g, o, x, splits=[3, 1, 17, 2, 18])
+    assert_same(yg, yo, name)
