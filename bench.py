@@ -57,13 +57,17 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons sampled under the bench load (B200_PROFILING.md recipe).  The sampler runs from before
+    the warm-up; samples are time-stamped and the ones inside the timed region are reported.  A default run's timed region is
+    ~0.1 s (a few sampler periods), so when fewer than 3 samples fall inside it the samples of the identical load right before
+    and after it (warm-up steps, untimed cool-down steps) are used as well and `window` says so."""
 
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+    Q = "timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
         self.index, self.proc, self.path = index, None, None
+        self.t_load0 = self.t0 = self.t1 = None
 
     def start(self):
         try:
@@ -75,7 +79,8 @@ class ClockSampler:
             self.proc = None
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        import datetime
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "window": None}
         if not self.proc:
             return out
         self.proc.terminate()
@@ -83,24 +88,30 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        rows = []
         try:
             for line in open(self.path):
                 f = [t.strip() for t in line.split(",")]
                 if len(f) < 9:
                     continue
                 try:
-                    sm.append(float(f[1])); mx.append(float(f[2]))
+                    ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    rows.append((ts, float(f[1]), float(f[2]), [v.lower().startswith("active") for v in f[5:9]]))
                 except ValueError:
                     continue
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
             os.unlink(self.path)
         except Exception:
             pass
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        inside = [r for r in rows if self.t0 is not None and self.t0 <= r[0] <= self.t1]
+        window = "timed region"
+        if len(inside) < 3:
+            inside = [r for r in rows if self.t_load0 is not None and r[0] >= self.t_load0]
+            window = "timed region plus the identical untimed load around it (warm-up, cool-down): the region is shorter than 3 sampler periods"
+        if inside:
+            reasons = sorted({n for r in inside for n, a in zip(names, r[3]) if a})
+            out.update(sm_mhz=float(np.median([r[1] for r in inside])), sm_max_mhz=float(max(r[2] for r in inside)), reasons=reasons,
+                       samples=len(inside), window=window)
         return out
 
 
@@ -277,23 +288,33 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    step()  # first touch (plan upload, allocations) before the sampler's load window
+    barrier()
+    clocks.t_load0 = time.time()
     for _ in range(args.warmup):
         step()
     barrier()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
     l0 = g.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     torch.cuda.profiler.start()  # cudaProfilerStart: `ncu --profile-from-start off` sees exactly the timed region
+    clocks.t0 = time.time()
     e0.record(stream)
     for _ in range(args.steps):
         step()
     e1.record(stream)
     barrier()
+    clocks.t1 = time.time()
     torch.cuda.profiler.stop()
     ms = e0.elapsed_time(e1)
     launches = g.launch_count() - l0
+    if clocks.t1 - clocks.t0 < 0.5:  # untimed cool-down under the same load so that the clock sampler sees it
+        t_end = time.time() + 0.5
+        while time.time() < t_end:
+            step()
+            torch.cuda.synchronize()
     clk = clocks.stop()
     ms = m.shard.max_over_ranks(ms, dev)  # multi-GPU timing rule: slowest rank
 

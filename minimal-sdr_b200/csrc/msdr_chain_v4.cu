@@ -40,6 +40,7 @@ namespace v4 {
 using namespace tc;
 
 constexpr int SPAN = 512;          // samples per FIR work item
+constexpr uint32_t kLead = 6;      // spans the FIR producers may run ahead of the chains (148 items in flight are ~5 spans by themselves)
 constexpr int UNIT = 128;          // samples per readiness counter: a chain starts on a span after its first two tiles
 // chain sub-tile ring: one slot being filtered by warp A, one by warp B, one draining to `out`, two landing.  With fewer
 // slots the load of a sub-tile can only be issued when it is already needed and its latency (~2 k cycles) is paid per sub-tile.
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
     uint32_t q = 0;     // pairs converted so far by this CTA (ring position q % ring, phase q / ring)
     uint32_t ntile = 0; // tiles processed so far by this CTA (TMEM hand-off phases)
     int cur_set = -1;
-    uint32_t cur_wave = 0, wave_item0 = 0; // claiming thread only
+    uint32_t cur_wave = 0, wave_item0 = 0, wave_spans0 = 0; // claiming thread only
     const uint32_t n_tiles = p.L / N;
     for (uint32_t iter = 0;; ++iter) {
       if (is_mma && lane == 0) {
@@ -208,13 +209,26 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
         if (it < p.n_items) {
           for (;;) { // items are claimed in increasing order: walk the waves forward
             const uint32_t nrb = p.tc_wave_rb0[cur_wave + 1] - p.tc_wave_rb0[cur_wave];
+            const uint32_t wgroups = min(p.W, p.NG - cur_wave * p.W); // chains of this wave
             if (it - wave_item0 < nrb * p.NT) {
               const uint32_t rem = it - wave_item0;
               span = (int)(rem / nrb);
               rb = (int)(p.tc_wave_rb0[cur_wave] + (rem - (uint32_t)span * nrb));
+              // flow control: the demodulated intermediate lives in `out` and should still be in L2 when its chain reads it, so
+              // the producers stay at most kLead spans ahead of the chains (p.ctrl[1] counts the spans the loaders have taken;
+              // everything before a claimed item is being produced, so the chains always get to within one span of it)
+              if ((uint32_t)span > kLead) {
+                const int want = (int)(wave_spans0 + wgroups * ((uint32_t)span - kLead));
+                const long long t0 = clock64();
+                while (ld_relaxed_gpu(p.ctrl + 1) < want) {
+                  __nanosleep(256);
+                  if (clock64() - t0 > kWatchdogCycles) __trap();
+                }
+              }
               break;
             }
             wave_item0 += nrb * p.NT;
+            wave_spans0 += wgroups * p.NT;
             ++cur_wave;
           }
         }
@@ -576,7 +590,10 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
             }
           }
           __syncwarp();
-          if (lane == 0) mbar_arrive(isLoad ? &pc->ld_full[slot] : &pc->m_full[slot]);
+          if (lane == 0) {
+            mbar_arrive(isLoad ? &pc->ld_full[slot] : &pc->m_full[slot]);
+            if (isLoad && ((((k + 1) * SUB_FF) % SPAN) == 0 || k + 1 == nsub)) atomicAdd(p.ctrl + 1, 1); // flow control
+          }
           prof.lap(2);
         }
         if (fast && active) bq_store_ff(ff, p.bq, p.Cpad, obj, ch);
@@ -761,7 +778,10 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
           else if (issued - k - 1 == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
           else asm volatile("cp.async.wait_group 0;" ::: "memory");
           __syncwarp(); // every lane's copies of this sub-tile have landed
-          if (lane == 0) mbar_arrive(&pc->ld_full[slot]);
+          if (lane == 0) {
+            mbar_arrive(&pc->ld_full[slot]);
+            if ((((k + 1) * SUB) % SPAN) == 0 || k + 1 == nsub) atomicAdd(p.ctrl + 1, 1); // one more span taken (flow control)
+          }
           prof.lap(2);
         }
       } else {

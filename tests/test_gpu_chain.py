@@ -307,7 +307,7 @@ def test_every_kernel_shape_is_bit_exact(msdr, orc, K, variant, name):
     """All shapes of the fused kernel (option "variant") produce the oracle's bits: mixed modes, ragged updates, 4-stage cascades on
     some channels, full-range (wrapping) taps on others, extreme inputs, a partial last group."""
     rng = np.random.default_rng(variant)
-    modes = msdr.synth.mixed_modes(200) + [SYNCAM, AM, CW]
+    modes = msdr.synth.mixed_modes(200) + [USB, AM, CW]
     x = msdr.synth.batch(modes, 128 * 41)
     x[7] = rng.integers(-32768, 32768, x.shape[1], dtype=np.int16)
     x[8] = -32768

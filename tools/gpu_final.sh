@@ -8,4 +8,4 @@ bash tools/gpu_profile.sh
 ncu -i gpurun_out/prof_chain.ncu-rep --page raw --csv > gpurun_out/prof_chain_raw.csv 2>/dev/null
 ncu -i gpurun_out/prof_chain.ncu-rep --page source --csv > gpurun_out/prof_chain_src.csv 2>/dev/null
 python tools/ncu_src_summary.py gpurun_out/prof_chain_src.csv 25 > gpurun_out/prof_chain_src_summary.txt 2>&1
-python tools/ncu_metrics_json.py gpurun_out/prof_chain_raw.csv gpurun_out/chain_kernel_ncu_metrics.json "ncu --set full --clock-control none --import-source on -k regex:chain_kernel -s 2 -c 2 python bench.py --steps 1 --warmup 3 --no-cpu --e2e-steps 0 --seconds 1 (tools/gpu_profile.sh)"
+python tools/ncu_metrics_json.py gpurun_out/prof_chain_raw.csv gpurun_out/chain_kernel_ncu_metrics.json "ncu --set full --clock-control none --import-source on -k regex:chain_kernel -s 0 -c 1 python bench.py --steps 1 --warmup 3 --no-cpu --e2e-steps 0 --seconds 3 (tools/gpu_profile.sh): one launch of 4096 channels x 1024 blocks"
