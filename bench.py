@@ -207,7 +207,9 @@ def workload_config(args):
             "fs_hz": FS, "modes": "{AM,USB,LSB,CW}[c mod 4]", "fir": "sketch tables: AM 102 taps (bw 2800 @ 24 kHz design, used as-is), SSB/CW 86 taps",
             "biquads": "biquad1 low-pass (0.9*IF, Q 0.54) + biquad2 notch (fs/8, Q 15), integer Q2.30",
             "l2": "inputs (3.6 GB per step) and outputs far exceed the 126 MB L2; no explicit flush", "sharding": "independent channel shards per GPU",
-            "layout": getattr(args, "layout", "updates")}
+            "layout": getattr(args, "layout", "updates"),
+            **({"with_frontend": "raw 12-bit ADC codes through msdr_frontend_update_device (DC-block, amplifier, AGC) before every chain update"}
+               if getattr(args, "with_frontend", False) else {})}
 
 
 def main():
@@ -223,6 +225,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--with-frontend", action="store_true",
+                    help="study: feed raw 12-bit ADC codes through the front-end conditioning kernel (DC-block, amplifier, AGC; SURVEY 8f rank 1) "
+                         "in front of every chain update; the default line measures the north-star path only")
     ap.add_argument("--layout", choices=["updates", "rows"], default="updates",
                     help="device-resident input layout: 'updates' = one contiguous [channels][samples] batch per update (how a streaming "
                          "receiver holds its block batches), 'rows' = one 10 s row per channel, updates are column windows of it")
@@ -279,8 +284,21 @@ def main():
             del x
         torch.cuda.empty_cache()
 
+    fe = None
+    if args.with_frontend:
+        fe = m.Frontend(C, device=local_rank)
+        fe.set_stream(stream.cuda_stream)
+        adc = [(xi.to(torch.int32) // 16 + 2048).clamp_(0, 4095).to(torch.int16) for xi in (xs if args.layout != "rows" else [x])]
+        if args.layout == "rows":
+            adc_calls = [adc[0].data_ptr() + 2 * b0 * BLOCK for b0, nb in updates]
+        else:
+            adc_calls = [a.data_ptr() for a in adc]
+        torch.cuda.synchronize()
+
     def step():
-        for d_in, d_out, nb, stride in calls:
+        for i, (d_in, d_out, nb, stride) in enumerate(calls):
+            if fe is not None:  # raw codes -> conditioned IF samples, written over the chain's input buffer
+                fe.update_device(adc_calls[i], d_in, nb, stride)
             g.update_device(d_in, d_out, nb, stride)
 
     def barrier():
@@ -297,6 +315,7 @@ def main():
         step()
     barrier()
     l0 = g.launch_count()
+    fe_l0 = fe.launch_count() if fe is not None else 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     torch.cuda.profiler.start()  # cudaProfilerStart: `ncu --profile-from-start off` sees exactly the timed region
@@ -309,7 +328,7 @@ def main():
     clocks.t1 = time.time()
     torch.cuda.profiler.stop()
     ms = e0.elapsed_time(e1)
-    launches = g.launch_count() - l0
+    launches = g.launch_count() - l0 + ((fe.launch_count() - fe_l0) if fe is not None else 0)
     if clocks.t1 - clocks.t0 < 0.5:  # untimed cool-down under the same load so that the clock sampler sees it
         t_end = time.time() + 0.5
         while time.time() < t_end:

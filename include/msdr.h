@@ -176,6 +176,38 @@ int msdr_study_fir_demod_tc_time(int device, uint16_t numTaps, uint32_t rows, ui
  * (integers 0 .. 2^31-1, arm_sqrt_f32 of Minimal-SDR.ino:606); *mismatches must come back 0. */
 int msdr_study_sqrt_check(int device, uint64_t *mismatches);
 
+/* ---- front-end conditioning: what sits between the ADC and the receive chain in the sketch ---------------
+ * raw unsigned ADC codes -> DC-blocking high-pass (AudioInputAnalog::update, input_adc.cpp:198-212) -> AudioAmplifier gain
+ * (mixer.cpp:34-47,134-159) -> int16 IF samples for msdr_chain_update*; per block the sketch's AGC (Minimal-SDR.ino:445-515)
+ * moves the amplifier gain for the blocks that follow (zero queue latency in a batch).  agc_start / agc_max / agc_on are the
+ * sketch's AGC_start (0.25), AGC_Max (40) and AGC_on (.ino:94-100).  One object per batch of channels, state carried from
+ * update to update.  Known reference defect reproduced as "value dropped": every 26th block maximum is stored outside
+ * agc_buffer (.ino:481-482). */
+typedef struct msdr_frontend msdr_frontend;
+typedef struct msdr_frontend_state {
+  int32_t hpf_x1, hpf_y1;  /* input_adc.cpp:37-38 */
+  int32_t multiplier;      /* AudioAmplifier::multiplier (mixer.h:80) */
+  int32_t agc_idx;         /* .ino:451 */
+  float agc_val;           /* .ino:104 */
+  int16_t agc_buffer[25];  /* .ino:450 */
+  int16_t reserved;
+} msdr_frontend_state;
+int msdr_frontend_create(msdr_frontend **out, int device, uint32_t n_channels, float agc_start, float agc_max, int agc_on);
+void msdr_frontend_destroy(msdr_frontend *fe);
+int msdr_frontend_set_stream(msdr_frontend *fe, void *cuda_stream);
+int msdr_frontend_synchronize(msdr_frontend *fe);
+const char *msdr_frontend_last_error(const msdr_frontend *fe);
+/* AudioInputAnalog::init (input_adc.cpp:59-63): hpf_x1 = first reading << 14, hpf_y1 = 0 */
+int msdr_frontend_preset(msdr_frontend *fe, uint32_t ch0, uint32_t nch, uint16_t first_reading);
+/* host buffers [n_channels][stride] (synchronous) / device buffers (asynchronous on the object's stream; 16-byte aligned rows) */
+int msdr_frontend_update(msdr_frontend *fe, const uint16_t *adc, int16_t *out, uint32_t n_blocks, size_t stride);
+int msdr_frontend_update_device(msdr_frontend *fe, const uint16_t *d_adc, int16_t *d_out, uint32_t n_blocks, size_t stride);
+int msdr_frontend_get_state(msdr_frontend *fe, uint32_t ch, msdr_frontend_state *out);
+int msdr_frontend_set_state(msdr_frontend *fe, uint32_t ch, const msdr_frontend_state *in);
+uint64_t msdr_frontend_launch_count(const msdr_frontend *fe);
+/* AudioAmplifier::gain (mixer.h:75-79): clamp to +-32767, multiplier = (int32_t)(gain * 65536.0f) */
+int32_t msdr_amp_gain_multiplier(float gain);
+
 const char *msdr_version(void);
 
 #ifdef __cplusplus

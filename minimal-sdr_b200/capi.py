@@ -28,6 +28,18 @@ class ChannelState(C.Structure):
     ]
 
 
+class FrontendState(C.Structure):  # msdr_frontend_state
+    _fields_ = [
+        ("hpf_x1", C.c_int32),
+        ("hpf_y1", C.c_int32),
+        ("multiplier", C.c_int32),
+        ("agc_idx", C.c_int32),
+        ("agc_val", C.c_float),
+        ("agc_buffer", C.c_int16 * 25),
+        ("reserved", C.c_int16),
+    ]
+
+
 def lib_path():
     return os.path.join(_HERE, "csrc", "libmsdr.so")
 
@@ -66,6 +78,18 @@ SYMBOLS = {
     "msdr_op_fir_demod_tc": (C.c_int, [C.c_int, C.c_uint16, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_size_t]),
     "msdr_study_fir_demod_tc_time": (C.c_int, [C.c_int, C.c_uint16, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "msdr_study_sqrt_check": (C.c_int, [C.c_int, C.POINTER(C.c_uint64)]),
+    "msdr_frontend_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_uint32, C.c_float, C.c_float, C.c_int]),
+    "msdr_frontend_destroy": (None, [C.c_void_p]),
+    "msdr_frontend_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "msdr_frontend_synchronize": (C.c_int, [C.c_void_p]),
+    "msdr_frontend_last_error": (C.c_char_p, [C.c_void_p]),
+    "msdr_frontend_preset": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint16]),
+    "msdr_frontend_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_size_t]),
+    "msdr_frontend_update_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_size_t]),
+    "msdr_frontend_get_state": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(FrontendState)]),
+    "msdr_frontend_set_state": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(FrontendState)]),
+    "msdr_frontend_launch_count": (C.c_uint64, [C.c_void_p]),
+    "msdr_amp_gain_multiplier": (C.c_int32, [C.c_float]),
     "msdr_version": (C.c_char_p, []),
 }
 

@@ -1,0 +1,340 @@
+// msdr_frontend.cu — K4: front-end conditioning in front of the receive chain, batched over channels:
+//   raw unsigned ADC codes -> 1-pole DC-blocking high-pass in S1.30 (AudioInputAnalog::update, input_adc.cpp:198-212)
+//   -> AudioAmplifier gain with SSAT16 (mixer.cpp:34-47,134-159, mixer.h:75-79) -> int16 IF samples,
+//   and per 128-sample block the AGC of the sketch (Minimal-SDR.ino:445-515): block maximum of |x| through the halfword SIMD
+//   idiom, 25-block history, float gain law, new amplifier multiplier for the blocks that follow.
+// Signal order: adc1 -> amp_adc -> queue_adc (.ino:76-78), AGC(p_adc) on each block read from the queue (.ino:530-534).
+// Batch semantics: zero queue latency, block k+1 is amplified with the gain AGC set after block k.
+//
+// The high-pass is a truncating recurrence per sample and the AGC a feedback per block: serial in time per channel, parallel
+// over channels.  One warp owns 32 channels (lane = channel) for the whole call; blocks travel global -> shared (cp.async,
+// coalesced, double buffered) -> lane-per-row processing in place -> global.  Bound: per-sample dependent latency of the
+// recurrence (~25 cycles) for few channels, HBM (4 B per sample) for many.
+#include "msdr_device.cuh"
+#include "msdr_internal.h"
+#include "../../include/msdr.h"
+
+#include <string>
+#include <vector>
+
+namespace msdr {
+namespace fe {
+
+constexpr int kBlock = 128;                    // AUDIO_BLOCK_SAMPLES
+constexpr int kPitchW = kBlock / 2 + 4;        // shared row pitch in words (4 mod 32: conflict-free row-wise 128-bit access)
+constexpr int kAgcBuf = 25;                    // .ino:445
+constexpr int kCoefHpf = 1048300 << 10;        // input_adc.cpp:32, S1.30
+
+struct State { // one channel
+  int32_t hpf_x1, hpf_y1; // input_adc.cpp:37-38
+  int32_t mult;           // AudioAmplifier::multiplier
+  int32_t agc_idx;        // .ino:451
+  float agc_val;          // AGC_val
+  int16_t agc_buf[kAgcBuf];
+  int16_t pad;
+};
+static_assert(sizeof(State) == 72, "State layout is mirrored by msdr_frontend_state");
+
+__host__ __device__ inline int32_t amp_multiplier(float n) // AudioAmplifier::gain, mixer.h:75-79
+{
+  if (n > 32767.0f) n = 32767.0f;
+  else if (n < -32767.0f) n = -32767.0f;
+#ifdef __CUDA_ARCH__
+  return __float2int_rz(__fmul_rn(n, 65536.0f));
+#else
+  return (int32_t)(n * 65536.0f);
+#endif
+}
+
+// ARMv7E-M SSUB16 (sets APSR.GE[1:0] / [3:2] when the low / high halfword difference is >= 0) and SEL (bytes of `a` where GE is set)
+__device__ __forceinline__ uint32_t ssub16(int a, int b, uint32_t &ge)
+{
+  const int lo = (int)(short)(a & 0xFFFF) - (int)(short)(b & 0xFFFF), hi = (a >> 16) - (b >> 16);
+  ge = (lo >= 0 ? 3u : 0u) | (hi >= 0 ? 12u : 0u);
+  return ((uint32_t)hi << 16) | ((uint32_t)lo & 0xFFFFu);
+}
+__device__ __forceinline__ uint32_t sel(uint32_t a, uint32_t b, uint32_t ge)
+{
+  const uint32_t m = ((ge & 1u) ? 0x000000FFu : 0u) | ((ge & 2u) ? 0x0000FF00u : 0u) | ((ge & 4u) ? 0x00FF0000u : 0u) | ((ge & 8u) ? 0xFF000000u : 0u);
+  return (a & m) | (b & ~m);
+}
+
+// .ino:481-514 with the 26th-store defect resolved as in the oracle (value dropped); returns true when gain() was called
+__device__ __forceinline__ bool agc_update(State &s, uint32_t absmax, float agc_max)
+{
+  --s.agc_idx;
+  if (s.agc_idx >= 0) s.agc_buf[s.agc_idx] = (int16_t)absmax;
+  if (s.agc_idx < 0) s.agc_idx = kAgcBuf;
+  int m = 0;
+#pragma unroll
+  for (int i = 0; i < kAgcBuf; ++i) m += s.agc_buf[i];
+  const int d = m / kAgcBuf;
+  const float f = __fdiv_rn(16000.0f, __int2float_rn(d));
+  const float val = s.agc_val;
+  const float vf = __fmul_rn(val, f);
+  bool changed = false;
+  if ((double)f > 1.3) {
+    const float fagc = __fadd_rn(val, __fdiv_rn(vf, 1500.0f));
+    if (fagc < agc_max) { s.agc_val = fagc; changed = true; }
+  } else if ((double)val > 0.1) {
+    if ((double)f < 0.6) { s.agc_val = __fsub_rn(val, __fdiv_rn(vf, 50.0f)); changed = true; }
+    else if ((double)f < 0.7) { s.agc_val = __fsub_rn(val, __fdiv_rn(vf, 200.0f)); changed = true; }
+    else if ((double)f < 0.8) { s.agc_val = __fsub_rn(val, __fdiv_rn(vf, 2000.0f)); changed = true; }
+    else if ((double)f < 0.9) { s.agc_val = __fsub_rn(val, __fdiv_rn(vf, 4000.0f)); changed = true; }
+  }
+  if (changed) s.mult = amp_multiplier(s.agc_val);
+  return changed;
+}
+
+struct Params {
+  const uint16_t *adc; // [C][stride] raw codes
+  int16_t *out;        // [C][stride]
+  size_t stride;
+  uint32_t C, n_blocks;
+  State *state;        // [C]
+  float agc_max;
+  int agc_on;
+};
+
+__global__ void __launch_bounds__(32) frontend_kernel(const Params p)
+{
+  __shared__ __align__(16) uint32_t buf[2][kGroup * kPitchW];
+  const int lane = threadIdx.x;
+  const uint32_t g = blockIdx.x, row = g * kGroup + lane;
+  const bool active = row < p.C;
+  const int nrows = min(kGroup, (int)(p.C - g * kGroup));
+  State s;
+  if (active) s = p.state[row];
+
+  // coalesced mapping for the copies: 2 rows of 256 bytes per warp instruction
+  const int r0 = lane >> 4, c = lane & 15;
+  const unsigned char *gin = reinterpret_cast<const unsigned char *>(p.adc + ((size_t)g * kGroup + r0) * p.stride) + c * 16;
+  unsigned char *gout = reinterpret_cast<unsigned char *>(p.out + ((size_t)g * kGroup + r0) * p.stride) + c * 16;
+  const size_t gstep = 2 * p.stride * 2;
+  auto issue = [&](uint32_t b) {
+    const uint32_t sdst = smem_u32(buf[b & 1]) + (uint32_t)(r0 * kPitchW * 4 + c * 16);
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (r0 + 2 * j < nrows)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst + (uint32_t)(j * 2 * kPitchW * 4)), "l"(gin + (size_t)b * kBlock * 2 + (size_t)j * gstep) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  issue(0);
+  for (uint32_t b = 0; b < p.n_blocks; ++b) {
+    if (b + 1 < p.n_blocks) { issue(b + 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    uint32_t *rowp = buf[b & 1] + lane * kPitchW;
+    if (active) {
+      int x1 = s.hpf_x1, y1 = s.hpf_y1;
+      const int mult = s.mult;
+      uint32_t maxv = (uint32_t)(-32767), minv = 32767u; // .ino:457-458, as packed halfword pairs
+#pragma unroll 1
+      for (int q = 0; q < kBlock / 8; ++q) {
+        uint4 v = *reinterpret_cast<const uint4 *>(rowp + 4 * q);
+        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          int o[2];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int tmp = (int)(((w[i] >> (16 * h)) & 0xFFFFu) << 14);
+            const int acc = (int)((uint32_t)y1 - (uint32_t)x1 + (uint32_t)tmp);
+            y1 = (int)(((long long)acc * (long long)kCoefHpf) >> 30); // FRACMUL_SHL(acc, COEF, 1): bits [61:30] of the product
+            x1 = tmp;
+            int sv = ssat16(y1 >> 14);
+            if (mult == 0) sv = 0;
+            else if (mult != 65536) sv = ssat16((int)(((long long)mult * (long long)sv) >> 16));
+            o[h] = sv;
+          }
+          w[i] = ((uint32_t)o[0] & 0xFFFFu) | ((uint32_t)o[1] << 16);
+          maxv = __vmaxs2(maxv, w[i]); // SSUB16 + SEL: per-halfword signed maximum / minimum
+          minv = __vmins2(minv, w[i]);
+        }
+        *reinterpret_cast<uint4 *>(rowp + 4 * q) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+      s.hpf_x1 = x1; s.hpf_y1 = y1;
+      if (p.agc_on) {
+        // .ino:468-478, literally: the cross-halfword compares, abs() of the whole words, the final select
+        int mx = (int)maxv, mn = (int)minv;
+        uint32_t ge;
+        (void)ssub16(mx, mx >> 16, ge); mx = (int)sel((uint32_t)mx, (uint32_t)(mx >> 16), ge); // max of the two halfwords -> low half
+        (void)ssub16(mn >> 16, mn, ge); mn = (int)sel((uint32_t)mn, (uint32_t)(mn >> 16), ge); // min -> low half
+        mn = (int)(mn < 0 ? 0u - (uint32_t)mn : (uint32_t)mn);                                   // abs() of the WHOLE words
+        mx = (int)(mx < 0 ? 0u - (uint32_t)mx : (uint32_t)mx);
+        (void)ssub16(mx, mn, ge);
+        const uint32_t absmax = sel((uint32_t)mx, (uint32_t)mn, ge) & 0xFFFFu;
+        agc_update(s, absmax, p.agc_max);
+      }
+    }
+    __syncwarp();
+    { // write the block back, coalesced
+      const unsigned char *ssrc = reinterpret_cast<const unsigned char *>(buf[b & 1]) + r0 * kPitchW * 4 + c * 16;
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (r0 + 2 * j < nrows)
+          *reinterpret_cast<uint4 *>(gout + (size_t)b * kBlock * 2 + (size_t)j * gstep) = *reinterpret_cast<const uint4 *>(ssrc + j * 2 * kPitchW * 4);
+    }
+    __syncwarp(); // buf[b & 1] is the target of the copy issued in the next iteration but one
+  }
+  if (active) p.state[row] = s;
+}
+
+} // namespace fe
+} // namespace msdr
+
+// ------------------------------------------------------------------------------------------------------------------------
+struct msdr_frontend {
+  int device = 0;
+  uint32_t C = 0;
+  float agc_start = 0.25f, agc_max = 40.0f;
+  int agc_on = 1;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  msdr::fe::State *d_state = nullptr;
+  uint16_t *d_in = nullptr;
+  int16_t *d_out = nullptr;
+  size_t stage_samples = 0;
+  uint64_t launches = 0;
+  std::string err;
+};
+
+namespace {
+thread_local std::string g_fe_error;
+int fe_fail(msdr_frontend *f, int code, const std::string &msg) { if (f) f->err = msg; else g_fe_error = msg; return code; }
+#define FCK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fe_fail(fe, MSDR_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); } while (0)
+}
+
+extern "C" {
+
+const char *msdr_frontend_last_error(const msdr_frontend *fe) { return fe ? fe->err.c_str() : g_fe_error.c_str(); }
+
+int msdr_frontend_create(msdr_frontend **out, int device, uint32_t n_channels, float agc_start, float agc_max, int agc_on)
+{
+  if (!out || n_channels == 0) return fe_fail(nullptr, MSDR_ERR_ARGUMENT, "frontend_create: bad arguments");
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fe_fail(nullptr, MSDR_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+  if (device < 0 || device >= ndev) return fe_fail(nullptr, MSDR_ERR_ARGUMENT, "frontend_create: bad device");
+  msdr_frontend *fe = new msdr_frontend();
+  fe->device = device; fe->C = n_channels; fe->agc_start = agc_start; fe->agc_max = agc_max; fe->agc_on = agc_on;
+  cudaError_t e = cudaSetDevice(device);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&fe->own_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaMalloc(&fe->d_state, (size_t)n_channels * sizeof(msdr::fe::State));
+  if (e != cudaSuccess) { g_fe_error = std::string("frontend_create: ") + cudaGetErrorString(e); delete fe; return MSDR_ERR_CUDA; }
+  fe->stream = fe->own_stream;
+  std::vector<msdr::fe::State> h(n_channels);
+  for (auto &s : h) {
+    s = msdr::fe::State{};
+    s.agc_idx = msdr::fe::kAgcBuf;                    // .ino:451
+    s.agc_val = agc_start;                            // .ino:104
+    s.mult = msdr::fe::amp_multiplier(agc_start);     // .ino:385
+  }
+  e = cudaMemcpy(fe->d_state, h.data(), h.size() * sizeof(msdr::fe::State), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { g_fe_error = std::string("frontend_create: ") + cudaGetErrorString(e); cudaFree(fe->d_state); delete fe; return MSDR_ERR_CUDA; }
+  *out = fe;
+  return MSDR_OK;
+}
+
+void msdr_frontend_destroy(msdr_frontend *fe)
+{
+  if (!fe) return;
+  cudaSetDevice(fe->device);
+  if (fe->stream) cudaStreamSynchronize(fe->stream);
+  cudaFree(fe->d_state); cudaFree(fe->d_in); cudaFree(fe->d_out);
+  if (fe->own_stream) cudaStreamDestroy(fe->own_stream);
+  delete fe;
+}
+
+int msdr_frontend_set_stream(msdr_frontend *fe, void *cuda_stream)
+{
+  if (!fe) return MSDR_ERR_ARGUMENT;
+  fe->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : fe->own_stream;
+  return MSDR_OK;
+}
+
+int msdr_frontend_synchronize(msdr_frontend *fe)
+{
+  if (!fe) return MSDR_ERR_ARGUMENT;
+  FCK(cudaSetDevice(fe->device));
+  FCK(cudaStreamSynchronize(fe->stream));
+  return MSDR_OK;
+}
+
+/* AudioInputAnalog::init (input_adc.cpp:59-63): x1 = first reading << 14, y1 = 0 */
+int msdr_frontend_preset(msdr_frontend *fe, uint32_t ch0, uint32_t nch, uint16_t first_reading)
+{
+  if (!fe || (uint64_t)ch0 + nch > fe->C) return fe_fail(fe, MSDR_ERR_ARGUMENT, "frontend_preset: bad channel range");
+  FCK(cudaSetDevice(fe->device));
+  FCK(cudaStreamSynchronize(fe->stream));
+  std::vector<msdr::fe::State> h(nch);
+  if (nch == 0) return MSDR_OK;
+  FCK(cudaMemcpy(h.data(), fe->d_state + ch0, nch * sizeof(msdr::fe::State), cudaMemcpyDeviceToHost));
+  for (auto &s : h) { s.hpf_x1 = (int32_t)((uint32_t)first_reading << 14); s.hpf_y1 = 0; }
+  FCK(cudaMemcpy(fe->d_state + ch0, h.data(), nch * sizeof(msdr::fe::State), cudaMemcpyHostToDevice));
+  return MSDR_OK;
+}
+
+int msdr_frontend_update_device(msdr_frontend *fe, const uint16_t *d_adc, int16_t *d_out, uint32_t n_blocks, size_t stride)
+{
+  if (!fe) return MSDR_ERR_ARGUMENT;
+  if (n_blocks == 0) return MSDR_OK;
+  if (!d_adc || !d_out || (uint64_t)n_blocks * MSDR_BLOCK_SAMPLES > stride) return fe_fail(fe, MSDR_ERR_ARGUMENT, "frontend_update: bad buffers / stride < n_blocks*128");
+  if (((uintptr_t)d_adc & 15u) || ((uintptr_t)d_out & 15u) || (stride & 7u))
+    return fe_fail(fe, MSDR_ERR_ARGUMENT, "frontend_update_device: buffers must be 16-byte aligned and stride a multiple of 8 samples");
+  FCK(cudaSetDevice(fe->device));
+  msdr::fe::Params p{};
+  p.adc = d_adc; p.out = d_out; p.stride = stride; p.C = fe->C; p.n_blocks = n_blocks; p.state = fe->d_state;
+  p.agc_max = fe->agc_max; p.agc_on = fe->agc_on;
+  msdr::fe::frontend_kernel<<<(fe->C + msdr::kGroup - 1) / msdr::kGroup, 32, 0, fe->stream>>>(p);
+  FCK(cudaGetLastError());
+  fe->launches++;
+  return MSDR_OK;
+}
+
+int msdr_frontend_update(msdr_frontend *fe, const uint16_t *adc, int16_t *out, uint32_t n_blocks, size_t stride)
+{
+  if (!fe) return MSDR_ERR_ARGUMENT;
+  if (n_blocks == 0) return MSDR_OK;
+  if (!adc || !out || (uint64_t)n_blocks * MSDR_BLOCK_SAMPLES > stride) return fe_fail(fe, MSDR_ERR_ARGUMENT, "frontend_update: bad buffers / stride < n_blocks*128");
+  FCK(cudaSetDevice(fe->device));
+  const size_t L = (size_t)n_blocks * MSDR_BLOCK_SAMPLES, need = (size_t)fe->C * L;
+  if (need > fe->stage_samples) {
+    FCK(cudaStreamSynchronize(fe->stream));
+    cudaFree(fe->d_in); cudaFree(fe->d_out);
+    fe->d_in = nullptr; fe->d_out = nullptr; fe->stage_samples = 0;
+    FCK(cudaMalloc(&fe->d_in, need * 2));
+    FCK(cudaMalloc(&fe->d_out, need * 2));
+    fe->stage_samples = need;
+  }
+  FCK(cudaMemcpy2DAsync(fe->d_in, L * 2, adc, stride * 2, L * 2, fe->C, cudaMemcpyHostToDevice, fe->stream));
+  int st = msdr_frontend_update_device(fe, fe->d_in, fe->d_out, n_blocks, L);
+  if (st != MSDR_OK) return st;
+  FCK(cudaMemcpy2DAsync(out, stride * 2, fe->d_out, L * 2, L * 2, fe->C, cudaMemcpyDeviceToHost, fe->stream));
+  FCK(cudaStreamSynchronize(fe->stream));
+  return MSDR_OK;
+}
+
+int msdr_frontend_get_state(msdr_frontend *fe, uint32_t ch, msdr_frontend_state *out)
+{
+  if (!fe || !out || ch >= fe->C) return MSDR_ERR_ARGUMENT;
+  static_assert(sizeof(msdr_frontend_state) == sizeof(msdr::fe::State), "public and device state layouts must match");
+  FCK(cudaSetDevice(fe->device));
+  FCK(cudaStreamSynchronize(fe->stream));
+  FCK(cudaMemcpy(out, fe->d_state + ch, sizeof(*out), cudaMemcpyDeviceToHost));
+  return MSDR_OK;
+}
+
+int msdr_frontend_set_state(msdr_frontend *fe, uint32_t ch, const msdr_frontend_state *in)
+{
+  if (!fe || !in || ch >= fe->C) return MSDR_ERR_ARGUMENT;
+  FCK(cudaSetDevice(fe->device));
+  FCK(cudaStreamSynchronize(fe->stream));
+  FCK(cudaMemcpy(fe->d_state + ch, in, sizeof(*in), cudaMemcpyHostToDevice));
+  return MSDR_OK;
+}
+
+uint64_t msdr_frontend_launch_count(const msdr_frontend *fe) { return fe ? fe->launches : 0; }
+
+int32_t msdr_amp_gain_multiplier(float gain) { return msdr::fe::amp_multiplier(gain); }
+
+} // extern "C"

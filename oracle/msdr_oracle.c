@@ -355,3 +355,176 @@ int orc_chain_run(orc_chain *c, const int16_t *in, int16_t *out, uint32_t n_bloc
   }
   return used;
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Front-end conditioning: ADC DC-blocking high-pass, AudioAmplifier gain, block-maximum AGC.
+ * Signal order in the sketch: adc1 -> amp_adc -> queue_adc (Minimal-SDR.ino:76-78); AGC(p_adc) is called on every
+ * block read from the queue, before the mix (.ino:530-534), and moves amp_adc.gain() for the blocks that follow.
+ * Batch semantics here: zero queue latency, i.e. block k+1 is amplified with the gain AGC set after block k.
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+#define ORC_COEF_HPF_DCBLOCK (1048300 << 10) /* input_adc.cpp:32, S1.30 */
+#define ORC_AGCBUF 25                        /* .ino:445 */
+
+/* FRACMUL_SHL(x, y, 1) (dspinst.h:358-368): SMULL, then hi << 2 | lo >> 30 */
+static inline int32_t orc_fracmul_shl1(int32_t x, int32_t y)
+{
+  const int64_t p = (int64_t)x * y;
+  return (int32_t)(((uint32_t)(int32_t)(p >> 32) << 2) | ((uint32_t)p >> 30));
+}
+
+/* input_adc.cpp:198-211.  in: raw unsigned ADC codes; state x1/y1 (input_adc.cpp:37-38; begin() presets x1 to the first
+ * reading << 14 and y1 to 0, :59-63 - the caller does that). */
+void orc_adc_hpf(const uint16_t *in, int16_t *out, uint32_t n, int32_t *hpf_x1, int32_t *hpf_y1)
+{
+  int32_t x1 = *hpf_x1, y1 = *hpf_y1;
+  for (uint32_t i = 0; i < n; i++) {
+    const int32_t tmp = (int32_t)((uint32_t)in[i] << 14);
+    int32_t acc = (int32_t)((uint32_t)y1 - (uint32_t)x1);
+    acc = (int32_t)((uint32_t)acc + (uint32_t)tmp);
+    y1 = orc_fracmul_shl1(acc, ORC_COEF_HPF_DCBLOCK);
+    x1 = tmp;
+    out[i] = (int16_t)orc_ssat16(y1 >> 14); /* signed_saturate_rshift(y1, 16, 14) */
+  }
+  *hpf_x1 = x1; *hpf_y1 = y1;
+}
+
+/* AudioAmplifier::gain (mixer.h:75-79) */
+int32_t orc_amp_multiplier(float n)
+{
+  if (n > 32767.0f) n = 32767.0f;
+  else if (n < -32767.0f) n = -32767.0f;
+  return (int32_t)(n * 65536.0f);
+}
+
+/* AudioAmplifier::update (mixer.cpp:134-159) + applyGain (:34-47).  mult == 0: the reference transmits NO block at all;
+ * a batch has to put something there - zeros, returned 0 so the caller can tell. */
+int orc_amp_apply(int16_t *data, uint32_t n, int32_t mult)
+{
+  if (mult == 0) { memset(data, 0, n * sizeof(int16_t)); return 0; }
+  if (mult == 65536) return 1;
+  for (uint32_t i = 0; i < n; i++)
+    data[i] = (int16_t)orc_ssat16((int32_t)(((int64_t)mult * data[i]) >> 16)); /* SMULWB/T, SSAT #16 */
+  return 1;
+}
+
+/* ARMv7E-M SIMD helpers used by AGC(): SSUB16 sets APSR.GE[1:0] / [3:2] when the low / high halfword difference is >= 0,
+ * SEL picks bytes of the first operand where GE is set. */
+static inline uint32_t orc_ssub16(uint32_t a, uint32_t b, uint32_t *ge)
+{
+  const int32_t lo = (int16_t)(a & 0xFFFF) - (int16_t)(b & 0xFFFF), hi = (int16_t)(a >> 16) - (int16_t)(b >> 16);
+  *ge = (lo >= 0 ? 3u : 0u) | (hi >= 0 ? 12u : 0u);
+  return ((uint32_t)hi << 16) | ((uint32_t)lo & 0xFFFFu);
+}
+static inline uint32_t orc_sel(uint32_t a, uint32_t b, uint32_t ge)
+{
+  const uint32_t m = ((ge & 1u) ? 0x000000FFu : 0u) | ((ge & 2u) ? 0x0000FF00u : 0u) | ((ge & 4u) ? 0x00FF0000u : 0u) | ((ge & 8u) ? 0xFF000000u : 0u);
+  return (a & m) | (b & ~m);
+}
+
+typedef struct {
+  int16_t buf[ORC_AGCBUF];
+  int idx;     /* .ino:451: starts at AGCBUF_SIZE */
+  float val;   /* AGC_val, .ino:104 */
+  float max;   /* AGC_Max, .ino:95 */
+  int on;      /* AGC_on, .ino:100 */
+} orc_agc;
+
+void orc_agc_init(orc_agc *a, float start, float max, int on)
+{
+  memset(a, 0, sizeof(*a));
+  a->idx = ORC_AGCBUF; a->val = start; a->max = max; a->on = on;
+}
+
+/* .ino:453-479: block maximum of |x| with the halfword SIMD idiom, literally (note abs() of whole 32-bit words whose upper
+ * halves hold left-overs of the parallel compare). */
+uint16_t orc_agc_absmax(const int16_t *block)
+{
+  const uint32_t *p = (const uint32_t *)block;
+  int minv = 32767, maxv = -minv;
+  uint32_t ge;
+  for (int i = 0; i < ORC_BLOCK / 2; i++) {
+    const uint32_t data = p[i];
+    (void)orc_ssub16((uint32_t)maxv, data, &ge); maxv = (int)orc_sel((uint32_t)maxv, data, ge);
+    (void)orc_ssub16(data, (uint32_t)minv, &ge); minv = (int)orc_sel((uint32_t)minv, data, ge);
+  }
+  (void)orc_ssub16((uint32_t)maxv, (uint32_t)(maxv >> 16), &ge); maxv = (int)orc_sel((uint32_t)maxv, (uint32_t)(maxv >> 16), ge);
+  (void)orc_ssub16((uint32_t)(minv >> 16), (uint32_t)minv, &ge); minv = (int)orc_sel((uint32_t)minv, (uint32_t)(minv >> 16), ge);
+  minv = (int)(minv < 0 ? 0u - (uint32_t)minv : (uint32_t)minv); /* abs(), INT_MIN stays INT_MIN like the ARM code */
+  maxv = (int)(maxv < 0 ? 0u - (uint32_t)maxv : (uint32_t)maxv);
+  (void)orc_ssub16((uint32_t)maxv, (uint32_t)minv, &ge);
+  return (uint16_t)orc_sel((uint32_t)maxv, (uint32_t)minv, ge);
+}
+
+/* .ino:481-514.  Returns 1 and the new amplifier multiplier in *mult when amp_adc.gain() was called.
+ * Reference defect kept visible: `agc_buffer[--agc_idx] = absmax; if (agc_idx < 0) agc_idx = AGCBUF_SIZE;` (.ino:481-482)
+ * stores every 26th value at index -1, outside the array (undefined behaviour).  Here, and in the compiled reference
+ * (oracle/Makefile gives the array a guard element in front), that store lands nowhere: the value is dropped. */
+int orc_agc_update(orc_agc *a, uint16_t absmax, int32_t *mult)
+{
+  if (!a->on) return 0;
+  --a->idx;
+  if (a->idx >= 0) a->buf[a->idx] = (int16_t)absmax;
+  if (a->idx < 0) a->idx = ORC_AGCBUF;
+  int m = 0;
+  for (int i = 0; i < ORC_AGCBUF; i++) m += a->buf[i];
+  const int d = m / ORC_AGCBUF;
+  const float x = 16000;
+  const float f = x / d;
+  int changed = 0;
+  if (f > 1.3) {
+    const float fagc = a->val + (a->val * f / 1500);
+    if (fagc < a->max) { a->val = fagc; changed = 1; }
+  } else if (a->val > 0.1) {
+    if (f < 0.6) { a->val = a->val - (a->val * f / 50); changed = 1; }
+    else if (f < 0.7) { a->val = a->val - (a->val * f / 200); changed = 1; }
+    else if (f < 0.8) { a->val = a->val - (a->val * f / 2000); changed = 1; }
+    else if (f < 0.9) { a->val = a->val - (a->val * f / 4000); changed = 1; }
+  }
+  if (changed) *mult = orc_amp_multiplier(a->val);
+  return changed;
+}
+
+typedef struct {
+  int32_t hpf_x1, hpf_y1;
+  int32_t mult;
+  orc_agc agc;
+} orc_frontend;
+
+orc_frontend *orc_frontend_new(uint32_t n_channels, float agc_start, float agc_max, int agc_on)
+{
+  orc_frontend *f = (orc_frontend *)calloc(n_channels ? n_channels : 1, sizeof(orc_frontend));
+  for (uint32_t i = 0; f && i < n_channels; i++) {
+    orc_agc_init(&f[i].agc, agc_start, agc_max, agc_on);
+    f[i].mult = orc_amp_multiplier(agc_start); /* .ino:385 */
+  }
+  return f;
+}
+void orc_frontend_free(orc_frontend *f) { free(f); }
+void orc_frontend_preset(orc_frontend *f, uint32_t ch, uint16_t first_reading) /* AudioInputAnalog::init, input_adc.cpp:59-63 */
+{
+  f[ch].hpf_x1 = (int32_t)((uint32_t)first_reading << 14);
+  f[ch].hpf_y1 = 0;
+}
+void orc_frontend_get(const orc_frontend *f, uint32_t ch, int32_t *x1, int32_t *y1, int32_t *mult, float *agc_val, int *agc_idx, int16_t *agc_buf)
+{
+  *x1 = f[ch].hpf_x1; *y1 = f[ch].hpf_y1; *mult = f[ch].mult; *agc_val = f[ch].agc.val; *agc_idx = f[ch].agc.idx;
+  memcpy(agc_buf, f[ch].agc.buf, sizeof(f[ch].agc.buf));
+}
+/* raw ADC codes [n_channels][stride] -> conditioned int16 IF samples, block by block: HPF, amplifier, AGC */
+void orc_frontend_run(orc_frontend *f, uint32_t n_channels, const uint16_t *adc, int16_t *out, uint32_t n_blocks, size_t stride)
+{
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+  for (long c = 0; c < (long)n_channels; c++) {
+    orc_frontend *k = &f[c];
+    for (uint32_t b = 0; b < n_blocks; b++) {
+      int16_t *o = out + (size_t)c * stride + (size_t)b * ORC_BLOCK;
+      orc_adc_hpf(adc + (size_t)c * stride + (size_t)b * ORC_BLOCK, o, ORC_BLOCK, &k->hpf_x1, &k->hpf_y1);
+      orc_amp_apply(o, ORC_BLOCK, k->mult);
+      int32_t m;
+      if (orc_agc_update(&k->agc, orc_agc_absmax(o), &m)) k->mult = m;
+    }
+  }
+}

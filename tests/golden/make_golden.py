@@ -90,6 +90,28 @@ def main():
         chain[f"y_q31_{q31}"] = y
         ch.close()
     np.savez_compressed(os.path.join(HERE, "chain_kat.npz"), **chain)
+
+    # front-end conditioning: the reference's DC-blocking loop, AudioAmplifier and AGC()
+    import frontend_lib as fl
+    rf = fl.Ref()
+    codes = np.concatenate([fl.adc_stream(1, 128 * 12, seed=11)[0], rng.integers(0, 65536, 128 * 4).astype(np.uint16),
+                            np.full(128 * 2, 65535, np.uint16), np.zeros(128 * 2, np.uint16)])
+    st0 = (int(codes[0]) << 14, 0)
+    hout, x1, y1 = rf.hpf(codes, *st0)
+    fe = {"hpf_in": codes, "hpf_state": np.array(st0, np.int64), "hpf_out": hout, "hpf_state_out": np.array([x1, y1], np.int64)}
+    blk = rng.integers(-32768, 32768, 128).astype(np.int16)
+    blk[:4] = [-32768, 32767, 0, -1]
+    gains = np.array([0.25, 0.9, 1.5, 40.0, 17.123, -2.0, 1e9], np.float32)
+    fe["amp_in"], fe["amp_gains"] = blk, gains
+    fe["amp_mults"] = np.array([rf.amp_multiplier(g) for g in gains], np.int64)
+    fe["amp_out"] = np.stack([rf.amp_block(g, blk)[0] for g in gains])
+    levels = np.abs(rng.normal(0, 1, 300)) * rng.choice([30, 300, 3000, 12000, 16000, 20000, 30000, 40000], 300)
+    ablocks = (rng.normal(0, 1, (300, 128)) * levels[:, None] * 0.4).clip(-32768, 32767).astype(np.int16)
+    ablocks[3] = 0
+    ablocks[4, 9] = -32768
+    fe["agc_blocks"] = ablocks
+    fe["agc_val"], fe["agc_mult"] = fl.Ref.agc_trajectory(ablocks, 0.25, 40.0)
+    np.savez_compressed(os.path.join(HERE, "frontend_kat.npz"), **fe)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
