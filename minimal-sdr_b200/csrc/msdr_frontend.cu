@@ -142,10 +142,9 @@ __global__ void __launch_bounds__(32) frontend_kernel(const Params p)
             const int acc = (int)((uint32_t)y1 - (uint32_t)x1 + (uint32_t)tmp);
             y1 = (int)(((long long)acc * (long long)kCoefHpf) >> 30); // FRACMUL_SHL(acc, COEF, 1): bits [61:30] of the product
             x1 = tmp;
-            int sv = ssat16(y1 >> 14);
-            if (mult == 0) sv = 0;
-            else if (mult != 65536) sv = ssat16((int)(((long long)mult * (long long)sv) >> 16));
-            o[h] = sv;
+            // AudioAmplifier::update special-cases multiplier 0 (nothing transmitted -> zeros here) and 65536 (pass-through,
+            // mixer.cpp:139-151); SSAT16((mult * s) >> 16) gives exactly those values for them, so no branch per sample
+            o[h] = ssat16((int)(((long long)mult * (long long)ssat16(y1 >> 14)) >> 16));
           }
           w[i] = ((uint32_t)o[0] & 0xFFFFu) | ((uint32_t)o[1] << 16);
           maxv = __vmaxs2(maxv, w[i]); // SSUB16 + SEL: per-halfword signed maximum / minimum
