@@ -59,3 +59,32 @@ def test_c3_sampled_parity_and_sharding(msdr, orc, K):
     torch.cuda.synchronize()
     assert torch.equal(y3, y[1024:2048])
     assert int(y.abs().max()) > 1000
+
+
+def test_two_waves_long_update_all_shapes_agree(msdr, orc, K):
+    """6000 channels = 188 groups = two waves of chains on 148 SMs, one update of 48 blocks = 12 spans (longer than the
+    producers' flow-control window): every kernel shape gives the same bytes, and sampled channels (both waves) match the oracle."""
+    import torch
+    C, nb = 6000, 48
+    dev = torch.device("cuda:0")
+    x = msdr.synth.torch_batch(C, nb * 128, dev)
+    outs = {}
+    for variant in (0, 256, 128, 64):
+        g, modes = _setup(msdr, K, C)
+        g.set_option("variant", variant)
+        y = torch.empty_like(x)
+        g.set_stream(torch.cuda.current_stream().cuda_stream)
+        g.update_device(x.data_ptr(), y.data_ptr(), nb, x.stride(0))
+        torch.cuda.synchronize()
+        outs[variant] = y
+        g.close()
+    for variant in (256, 128, 64):
+        assert torch.equal(outs[0], outs[variant]), f"variant {variant} differs from the default shape"
+    pick = [0, 31, 4735, 4736, 4737, 5000, 5999]
+    o = orc.chain(len(pick))
+    for i, c in enumerate(pick):
+        o.set_mode(i, 1, modes[c])
+        o.fir_init(i, 1, *tables_for(K, modes[c]))
+    o.biquad_set_coefficients(0, 0, len(pick), 0, K["biquad1_lowpass_coef"])
+    o.biquad_set_coefficients(1, 0, len(pick), 0, K["biquad2_notch_coef"])
+    assert_same(outs[0].cpu().numpy()[pick], o.run(np.ascontiguousarray(x.cpu().numpy()[pick]))[0], "two waves, sampled channels")
