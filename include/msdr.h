@@ -207,6 +207,9 @@ int msdr_frontend_set_state(msdr_frontend *fe, uint32_t ch, const msdr_frontend_
 uint64_t msdr_frontend_launch_count(const msdr_frontend *fe);
 /* AudioAmplifier::gain (mixer.h:75-79): clamp to +-32767, multiplier = (int32_t)(gain * 65536.0f) */
 int32_t msdr_amp_gain_multiplier(float gain);
+/* AudioAmplifier::update / applyGain (mixer.cpp:34-47,134-159) in place on host rows: SSAT16((multipliers[row] * x) >> 16).
+ * Multiplier 65536 leaves the data unchanged and 0 gives zeros (the reference transmits no block at all for 0). */
+int msdr_op_amplifier(int device, const int32_t *multipliers, int16_t *data, uint32_t rows, uint32_t n, size_t stride);
 
 const char *msdr_version(void);
 

@@ -396,6 +396,59 @@ private:
   bool dir, pass;
 };
 
+// ---- AudioAmplifier (mixer.{h,cpp}): the sketch's amp_adc / amp_dac ---------------------------------------------------------
+class AudioAmplifier : public AudioStream {
+public:
+  AudioAmplifier(void) : AudioStream(1, inputQueueArray), multiplier(65536) {}
+  void gain(float n) { multiplier = msdr_amp_gain_multiplier(n); } // mixer.h:75-79
+  int device = 0;
+  virtual void update(void)
+  {
+    if (multiplier == 0) { // zero gain: discard the input, transmit nothing (mixer.cpp:139-142)
+      audio_block_t *b = receiveReadOnly(0);
+      if (b) release(b);
+      return;
+    }
+    audio_block_t *block = multiplier == 65536 ? receiveReadOnly(0) : receiveWritable(0);
+    if (!block) return;
+    if (multiplier != 65536) {
+      std::vector<int32_t> m(block->channels, multiplier);
+      msdr_op_amplifier(device, m.data(), block->data, block->channels, AUDIO_BLOCK_SAMPLES, AUDIO_BLOCK_SAMPLES);
+    }
+    transmit(block);
+    release(block);
+  }
+private:
+  int32_t multiplier;
+  audio_block_t *inputQueueArray[1];
+};
+
+// ---- Frontend: adc1's DC-blocking filter + amp_adc + AGC() for a batch of channels in one object --------------------------
+// (AudioInputAnalog is Teensy hardware; what it does to the samples, input_adc.cpp:198-212, and what the sketch does with
+// them before demodulation(), .ino:76-78,445-515,534, is this.)  update() = one or more audio blocks of raw ADC codes.
+class Frontend {
+public:
+  explicit Frontend(uint32_t channels, int device = 0, float AGC_start = 0.25f, float AGC_Max = 40.0f, int AGC_on = 1) : n(channels), fe(nullptr)
+  {
+    if (msdr_frontend_create(&fe, device, channels, AGC_start, AGC_Max, AGC_on) != MSDR_OK) fe = nullptr;
+  }
+  ~Frontend() { msdr_frontend_destroy(fe); }
+  Frontend(const Frontend &) = delete;
+  Frontend &operator=(const Frontend &) = delete;
+  bool ok() const { return fe != nullptr; }
+  int begin(uint16_t first_reading) { return msdr_frontend_preset(fe, 0, n, first_reading); } // AudioInputAnalog::init, input_adc.cpp:59-63
+  int update(const uint16_t *codes, int16_t *p_adc, uint32_t n_blocks, size_t stride) { return msdr_frontend_update(fe, codes, p_adc, n_blocks, stride); }
+  float AGC_val(uint32_t channel = 0) const
+  {
+    msdr_frontend_state st;
+    return msdr_frontend_get_state(fe, channel, &st) == MSDR_OK ? st.agc_val : 0.0f;
+  }
+  msdr_frontend *handle() { return fe; }
+private:
+  uint32_t n;
+  msdr_frontend *fe;
+};
+
 // ---- Receiver: the sketch's FIR instances + demodulation() for a batch of channels, fused with the two biquads --------
 class Receiver {
 public:

@@ -749,6 +749,19 @@ int msdr_op_demod(int device, int kind, const int16_t *I, const int16_t *Q, int1
   return MSDR_OK;
 }
 
+int msdr_op_amplifier(int device, const int32_t *multipliers, int16_t *data, uint32_t rows, uint32_t n, size_t stride)
+{
+  if (!multipliers || !data || n > stride) return MSDR_ERR_ARGUMENT;
+  int st = op_begin(device); if (st) return st;
+  DevBuf d, m;
+  OPCK(d.alloc((size_t)rows * n * 2)); OPCK(m.alloc((size_t)rows * 4));
+  OPCK(cudaMemcpy2D(d.p, (size_t)n * 2, data, stride * 2, (size_t)n * 2, rows, cudaMemcpyHostToDevice));
+  OPCK(cudaMemcpy(m.p, multipliers, (size_t)rows * 4, cudaMemcpyHostToDevice));
+  OPCK(launch_amplifier(m.as<int32_t>(), d.as<int16_t>(), rows, n, n, nullptr));
+  OPCK(cudaMemcpy2D(data, stride * 2, d.p, (size_t)n * 2, (size_t)n * 2, rows, cudaMemcpyDeviceToHost));
+  return MSDR_OK;
+}
+
 int msdr_op_biquad(int device, int32_t *definition, int16_t *data, uint32_t rows, uint32_t n, size_t stride)
 {
   if (!definition || !data || (n & 1u) || n > stride) return MSDR_ERR_ARGUMENT;

@@ -136,6 +136,26 @@ cudaError_t launch_demod(int kind, const int16_t *I, const int16_t *Q, int16_t *
   return cudaGetLastError();
 }
 
+// ---- AudioAmplifier::update / applyGain (mixer.cpp:34-47,134-159): SSAT16((mult * x) >> 16), one multiplier per row --------
+// (multiplier 65536 passes data through and 0 yields zeros: exactly what the formula gives; the reference transmits no block
+// at all for 0, which a caller handles by not forwarding the block)
+__global__ void amplifier_kernel(const int32_t *__restrict__ mult, int16_t *__restrict__ data, uint32_t rows, uint32_t n, size_t stride)
+{
+  const size_t total = (size_t)rows * n;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / n, off = r * stride + (i - r * n);
+    data[off] = (int16_t)ssat16((int)(((long long)mult[r] * (long long)data[off]) >> 16));
+  }
+}
+cudaError_t launch_amplifier(const int32_t *mult, int16_t *data, uint32_t rows, uint32_t n, size_t stride, cudaStream_t s)
+{
+  const size_t total = (size_t)rows * n;
+  if (total == 0) return cudaSuccess;
+  const int grid = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+  amplifier_kernel<<<grid, 256, 0, s>>>(mult, data, rows, n, stride);
+  return cudaGetLastError();
+}
+
 // ---- AudioFilterBiquad::update (filter_biquad.cpp:33-82): one thread per stream, stage-major -----------
 __global__ void biquad_kernel(int32_t *__restrict__ definition, int16_t *__restrict__ data, uint32_t rows, uint32_t n, size_t stride)
 {

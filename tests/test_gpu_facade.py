@@ -68,3 +68,32 @@ def test_standalone_objects(msdr, orc, tmp_path):
             Q = I[::-1]
             ei, eq = orc.freq_conv(1 if b >= 2 else 0, 0 if b == NB - 1 else 1, I, Q, oscI, oscQ)
             assert np.array_equal(oi[c, b * 128:(b + 1) * 128], ei) and np.array_equal(oq[c, b * 128:(b + 1) * 128], eq), (c, b)
+
+
+def test_frontend_objects(msdr, tmp_path):
+    """Frontend (DC block + amp_adc + AGC) fed one audio block per call, and a stand-alone AudioAmplifier in an AudioConnection
+    graph, against the CPU checker (pinned to the reference's compiled code by tests/test_frontend_cpu.py)."""
+    import frontend_lib as fl
+    _build()
+    C, NB = 6, 40
+    codes = fl.adc_stream(C, NB * 128, seed=21)
+    codes.tofile(tmp_path / "codes.bin")
+    outs = [str(tmp_path / n) for n in ("fe.bin", "amp.bin", "agc.bin")]
+    r = subprocess.run([os.path.join(HOST, "frontend_objects"), str(C), str(NB), str(tmp_path / "codes.bin")] + outs, capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    ofe = np.fromfile(outs[0], np.int16).reshape(C, NB * 128)
+    oamp = np.fromfile(outs[1], np.int16).reshape(C, NB * 128)
+    agc = np.fromfile(outs[2], np.float32)
+    forc = fl.Orc()
+    o = forc.frontend(C)
+    for c in range(C):
+        o.preset(c, codes[0, 0])  # Frontend::begin presets every channel with the same first reading
+    assert np.array_equal(ofe, o.run(codes))
+    assert np.array_equal(agc.view(np.uint32), np.array([o.state(c)["agc_val"] for c in range(C)], np.float32).view(np.uint32))
+    x = codes.view(np.int16)
+    for b in range(NB):
+        gain = 1.7 if b < 3 else 1.0 if b == 3 else 0.0 if b == 4 else -0.33
+        for c in range(C):
+            exp, sent = forc.amp_apply(x[c, b * 128:(b + 1) * 128], forc.amp_multiplier(gain))
+            assert np.array_equal(oamp[c, b * 128:(b + 1) * 128], exp), (c, b)
