@@ -93,7 +93,7 @@ struct msdr_chain {
   uint64_t meta_version = 1;  // bumped whenever a channel's table binding or a table's contents change
   struct TcPlan {
     uint64_t version = 0;
-    uint32_t ch0 = 0, nch = 0, W = 0, K = 0, rings[3] = {0, 0, 0}, n_rb = 0, n_waves = 0;
+    uint32_t ch0 = 0, nch = 0, W = 0, K = 0, rings[4] = {0, 0, 0, 0}, n_rb = 0, n_waves = 0;
     bool usable = false;
     uint32_t *d_rowmap = nullptr, *d_grp = nullptr, *d_wave_rb0 = nullptr;
     uint4 *d_rb = nullptr;
@@ -485,14 +485,22 @@ int msdr_chain_update_range_device(msdr_chain *chain, uint32_t ch0, uint32_t nch
   if (use_tc) { // tensor-core FIR producers (msdr_chain_v4.cu)
     int sms = 0;
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, chain->device));
-    int st = build_tc_plan(chain, ch0, nch, (uint32_t)sms);
+    // more channel groups than SMs: two chain sets per SM (waves of 2 x SMs groups), unless a study variant asks for a
+    // specific shape (bits 7, 8) or forbids it (bit 9)
+    bool dual = NG > (uint32_t)sms && !(chain->variant & (128 | 256 | 512));
+    int st = build_tc_plan(chain, ch0, nch, (uint32_t)sms * (dual ? 2u : 1u));
     if (st != MSDR_OK) return st;
+    if (dual && chain->plan.usable && !chain->plan.rings[3]) { // the second set of chain slots does not fit next to this window
+      dual = false;
+      st = build_tc_plan(chain, ch0, nch, (uint32_t)sms);
+      if (st != MSDR_OK) return st;
+    }
     const msdr_chain::TcPlan &pl = chain->plan;
     use_tc = pl.usable;
     if (use_tc) {
       p.NG = NG;
       p.NT = (p.L + chain_v4_span_samples() - 1) / chain_v4_span_samples();
-      p.W = (uint32_t)sms;
+      p.W = pl.W; // chains per wave
       p.n_items = pl.n_rb * p.NT;
       p.tc_rowmap = pl.d_rowmap; p.tc_rb = pl.d_rb; p.tc_grp = pl.d_grp; p.tc_wave_rb0 = pl.d_wave_rb0; p.tc_bmat = pl.d_bmat;
       // kernel shape: post warps where they fit, else the plain classic shape; variant bit 7 asks for the FF chain side and
@@ -500,6 +508,7 @@ int msdr_chain_update_range_device(msdr_chain *chain, uint32_t ch0, uint32_t nch
       uint32_t shape = pl.rings[0] ? 0u : 1u;
       if ((chain->variant & 256) && pl.rings[1]) shape = 1u;
       if ((chain->variant & 128) && pl.rings[2]) shape = 2u;
+      if (dual) shape = 3u;
       p.tc_K = pl.K; p.tc_ring = pl.rings[shape]; p.tc_ff = shape;
       p.NU = p.L / chain_v4_unit_samples();
       const size_t n_cnt = (size_t)NG * p.NU;

@@ -53,13 +53,15 @@ constexpr int kThreads = 16 * 32;
 //   classic  load (warp 8) -> A -> B -> store: every warp runs whole biquad stages; 3 convert warps (7,12,13) and 4 post warps
 //            (10,11,14,15) that demodulate and write back what the epilogue warps drained, so that the epilogue warps, which
 //            the TMEM lane rule pins next to the chain warps, do as little as possible
+//   DUAL     classic without post warps, but TWO chain sets per SM (load 12 -> A 10 -> B 11 -> store 13 is the second): for more
+//            channel groups than SMs, where one chain pair per SM is the ceiling (~170 Gsamples/s); 3 convert warps (7,14,15)
 //   FF       the three input-side products of a stage do not depend on its output, so they are taken off the chain warps:
 //            load+FF1 (warp 10) -> A -> FF2 (warp 11) -> B -> store.  Warps 10/11 (sub-partitions 2, 3) hand the chain warps the
 //            feed-forward sums e[n] as 32-bit words and A/B run only the two recurrence products per sample
 //            (tools/microbench/bqstep2.cu: 35 instead of 45 cycles per step).  3 convert warps (7,14,15).
-template <bool FF, bool POST> struct Roles {
-  static_assert(!(FF && POST), "the FF shape has no warps left for post-processing");
-  static constexpr int NCONV = (FF || POST) ? 3 : 5;
+template <bool FF, bool POST, bool DUAL = false> struct Roles {
+  static_assert(!(FF && POST) && !(DUAL && (FF || POST)), "shapes are exclusive: every warp has one role");
+  static constexpr int NCONV = (FF || POST || DUAL) ? 3 : 5;
   static constexpr int NPOST = POST ? 4 : 0;     // warps 10,11,14,15 take demodulation + write-back off the epilogue warps
   static constexpr int NSTAGE = POST ? 2 : 1;    // staging buffers between epilogue and post warps
   static constexpr int kLive = (4 + 1 + NCONV + NPOST) * 32;
@@ -68,11 +70,20 @@ template <bool FF, bool POST> struct Roles {
   // converters wait on memory, not on issue slots: in the classic shape two of them sit next to the chain warps (12, 13)
   static __device__ __forceinline__ bool is_conv(int w)
   {
-    return FF ? (w == 7 || w == 14 || w == 15) : POST ? (w == 7 || w == 12 || w == 13) : (w == 7 || w == 10 || w == 11 || w == 14 || w == 15);
+    return (FF || DUAL) ? (w == 7 || w == 14 || w == 15) : POST ? (w == 7 || w == 12 || w == 13) : (w == 7 || w == 10 || w == 11 || w == 14 || w == 15);
   }
   static __device__ __forceinline__ int conv_index(int w)
   {
-    return FF ? (w == 7 ? 0 : w == 14 ? 1 : 2) : POST ? (w == 7 ? 0 : w == 12 ? 1 : 2) : (w == 7 ? 0 : w == 10 ? 1 : w == 11 ? 2 : w == 14 ? 3 : 4);
+    return (FF || DUAL) ? (w == 7 ? 0 : w == 14 ? 1 : 2) : POST ? (w == 7 ? 0 : w == 12 ? 1 : 2) : (w == 7 ? 0 : w == 10 ? 1 : w == 11 ? 2 : w == 14 ? 3 : 4);
+  }
+  // classic chain side: which chain set (0, or 1 in the DUAL shape) and which role (0 load, 1 A, 2 B, 3 store) a warp has
+  static __device__ __forceinline__ void chain_role(int w, int &set, int &role)
+  {
+    set = role = -1;
+    if (w == 8) { set = 0; role = 0; } else if (w == 4) { set = 0; role = 1; } else if (w == 5) { set = 0; role = 2; } else if (w == 9) { set = 0; role = 3; }
+    if (DUAL) { // the second chain pair sits on sub-partitions 2 and 3, its I/O warps on 0 and 1
+      if (w == 12) { set = 1; role = 0; } else if (w == 10) { set = 1; role = 1; } else if (w == 11) { set = 1; role = 2; } else if (w == 13) { set = 1; role = 3; }
+    }
   }
   static __device__ __forceinline__ bool is_post(int w) { return POST && (w == 10 || w == 11 || w == 14 || w == 15); }
   static __device__ __forceinline__ int post_index(int w) { return w == 10 ? 2 : w == 11 ? 3 : w == 14 ? 0 : 1; } // post warp i serves epilogue warp i
@@ -80,9 +91,9 @@ template <bool FF, bool POST> struct Roles {
 constexpr int NSLOT_FF = 7, SUB_FF = 64; // load, FF1, A, FF2, B, store each hold a slot in steady state; one more decouples them
 constexpr int EW = SUB_FF + 4, YW = SUB_FF / 2 + 4;                    // FF slot: e[n] rows (32-bit) and packed int16 rows, word pitches
 constexpr uint32_t kSlotBytesFF = kGroup * (EW + YW) * 4u;
-constexpr int NSLOT_MAX = 7;
+constexpr int NSLOT_MAX = 10; // FF: 7 slots; DUAL: 2 sets x 5
 __host__ __device__ inline uint32_t slot_bytes(uint32_t sub) { return kGroup * (sub / 2 + 4) * 4u; }
-constexpr uint32_t kCtrlBytes = 1280;
+constexpr uint32_t kCtrlBytes = 1536;
 
 
 struct __align__(16) Ctrl {
@@ -104,9 +115,9 @@ struct __align__(16) Ctrl {
 static_assert(sizeof(Ctrl) <= kCtrlBytes, "Ctrl must fit its smem slot");
 
 uint32_t sub_for(uint32_t K) { return K > 128 ? 64 : 128; }
-size_t smem_bytes(uint32_t K, uint32_t ring, bool ff, bool post)
+size_t smem_bytes(uint32_t K, uint32_t ring, bool ff, bool post, bool dual = false)
 {
-  const size_t slots = ff ? (size_t)NSLOT_FF * kSlotBytesFF : (size_t)NSLOT * slot_bytes(sub_for(K));
+  const size_t slots = ff ? (size_t)NSLOT_FF * kSlotBytesFF : (size_t)(dual ? 2 : 1) * NSLOT * slot_bytes(sub_for(K));
   return (size_t)kCtrlBytes + 4u * a_plane_bytes(ring) + 4u * N * K + (post ? 2u : 1u) * kStagingBytes + slots + 1024u;
 }
 
@@ -156,11 +167,11 @@ __device__ __forceinline__ void chain_span(BQ (&st)[1], uint4 *row, int nq)
   }
 }
 
-template <bool FF, bool POST>
+template <bool FF, bool POST, bool DUAL>
 __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
 {
   using BQ = BqStage;
-  using R = Roles<FF, POST>;
+  using R = Roles<FF, POST, DUAL>;
   constexpr int NCONV = R::NCONV, kLive = R::kLive, kLoadWarp = R::kLoadWarp;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // the operand rings want 128-byte alignment; round the dynamic window up to 1 KB to be independent of the static layout
@@ -652,16 +663,21 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
     }
     return;
   }
-  if (warp == kChainA || warp == kChainB) {
+  int cset, crole;
+  R::chain_role(warp, cset, crole);
+  if (cset < 0) return;
+  const int ci = cset * (int)gridDim.x + (int)blockIdx.x; // chain index: channel groups ci, ci + p.W, ... (p.W = chains per wave)
+  const int sbase = cset * NSLOT;                          // this set's barriers and ring slots
+  if (crole == 1 || crole == 2) {
     // ================================================================== biquad chain: warp A = object 1, warp B = object 2
-    const bool isA = (warp == kChainA);
+    const bool isA = (crole == 1);
     const int obj = isA ? 0 : 1;
     const int SUB = (int)p.tc_sub, BW = SUB / 2 + 4;
     const uint32_t kSlotBytes = slot_bytes(p.tc_sub);
     const int nsub = (int)((p.L + SUB - 1) / SUB);
-    Prof prof(p.prof, isA ? 3 : 4);
-    uint32_t pos = 0; // sub-tiles handled so far by this CTA's chain (ring position; identical in all four chain-side warps)
-    for (int g = (int)blockIdx.x; g < (int)p.NG; g += (int)p.W) {
+    Prof prof(cset == 0 ? p.prof : nullptr, isA ? 3 : 4);
+    uint32_t pos = 0; // sub-tiles handled so far by this chain set (ring position; identical in all four chain-side warps)
+    for (int g = ci; g < (int)p.NG; g += (int)p.W) {
       const uint32_t row = (uint32_t)(g * kGroup + lane), ch = p.ch0 + row;
       const bool active = row < p.C;
 
@@ -677,7 +693,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
       if (fast && active) bq_load_stage(st[0], fl, p.bq, p.Cpad, obj, 0, ch);
 
       for (int k = 0; k < nsub; ++k, ++pos) {
-        const int slot = (int)(pos % NSLOT);
+        const int slot = sbase + (int)(pos % NSLOT);
         const uint32_t phs = (pos / NSLOT) & 1u;
         prof.start();
         mbar_wait(isA ? &pc->ld_full[slot] : &pc->ab_full[slot], phs);
@@ -707,23 +723,23 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
       if (fast && active) bq_store_stage(st[0], fl, p.bq, p.Cpad, obj, 0, ch);
     }
     prof.flush();
-  } else if (warp == kLoadWarp || warp == kStoreWarp) {
+  } else {
     // ================================================================== chain I/O: sub-tiles `out` -> smem ring -> `out`
     // Plain coalesced 16-byte accesses by two dedicated warps (32 per-row bulk copies per direction kept the SM's copy engine
     // busier than the biquad itself).  A warp instruction covers 32 >> lg rows of 1 << lg chunks; all addresses advance by
     // constants, so a sub-tile costs 32 << lg >> 5 loads and stores per lane and little else.
-    const bool isLoad = (warp == kLoadWarp);
+    const bool isLoad = (crole == 0);
     const int SUB = (int)p.tc_sub, BW = SUB / 2 + 4;
     const uint32_t kSlotBytes = slot_bytes(p.tc_sub);
     const int nsub = (int)((p.L + SUB - 1) / SUB); // L is a multiple of 128 and SUB is 64 or 128: sub-tiles are always full
-    Prof prof(p.prof, isLoad ? 5 : 6);
+    Prof prof(cset == 0 ? p.prof : nullptr, isLoad ? 5 : 6);
     const int lg = SUB == 128 ? 4 : 3;           // log2 of the 16-byte chunks per row
     const int rpi = 32 >> lg, nins = kGroup / rpi; // rows per warp instruction, instructions per sub-tile
     const int r0 = lane >> lg, c = lane & ((1 << lg) - 1);
     const size_t gstep = (size_t)rpi * p.stride * 2u;  // bytes between the rows of consecutive instructions
     const uint32_t sstep = (uint32_t)rpi * BW * 4u;
     uint32_t pos = 0;
-    for (int g = (int)blockIdx.x; g < (int)p.NG; g += (int)p.W) {
+    for (int g = ci; g < (int)p.NG; g += (int)p.W) {
       const int nrows = min(kGroup, (int)p.C - g * kGroup);
       unsigned char *gp0 = reinterpret_cast<unsigned char *>(p.out + ((size_t)g * kGroup + r0) * p.stride) + c * 16;
       int ready = 0; // leading units known to be in `out` for every row of the group
@@ -753,7 +769,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
         // round trip to L2/HBM is off the chain's path
         constexpr int AHEAD = 2;
         auto issue = [&](int kk, uint32_t pp, bool blocking) -> bool {
-          const int sl = (int)(pp % NSLOT);
+          const int sl = sbase + (int)(pp % NSLOT);
           if (!unit_ready(kk, blocking)) return false;
           if (blocking) mbar_wait(&pc->slot_free[sl], ((pp / NSLOT) & 1u) ^ 1u);
           else if (!mbar_test_wait(&pc->slot_free[sl], ((pp / NSLOT) & 1u) ^ 1u)) return false;
@@ -767,7 +783,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
         };
         int issued = 0; // sub-tiles requested so far
         for (int k = 0; k < nsub; ++k, ++pos) {
-          const int slot = (int)(pos % NSLOT);
+          const int slot = sbase + (int)(pos % NSLOT);
           prof.start();
           if (issued <= k) { issue(k, pos, true); issued = k + 1; }
           prof.lap(0);
@@ -786,7 +802,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
         }
       } else {
         for (int k = 0; k < nsub; ++k, ++pos) {
-          const int slot = (int)(pos % NSLOT);
+          const int slot = sbase + (int)(pos % NSLOT);
           const uint32_t phs = (pos / NSLOT) & 1u;
           unsigned char *sp0 = bq_base + (uint32_t)slot * kSlotBytes + (uint32_t)r0 * BW * 4u + c * 16;
           unsigned char *gp = gp0 + (size_t)k * SUB * 2u;
@@ -842,15 +858,16 @@ uint32_t chain_v4_unit_samples() { return v4::UNIT; }
 //   shape 0  classic chain side + post warps (two staging buffers)     -- the default where it fits
 //   shape 1  classic chain side, epilogue warps demodulate themselves  -- long windows (256 taps)
 //   shape 2  FF chain side                                             -- opt-in (variant bit 7)
+//   shape 3  two chain sets per SM, no post warps                      -- more channel groups than SMs
 // rings[s] = 0: shape s does not fit.  false = the tensor-core form does not apply at all.
-bool chain_v4_config(uint32_t K, int smem_max, uint32_t rings[3])
+bool chain_v4_config(uint32_t K, int smem_max, uint32_t rings[4])
 {
-  rings[0] = rings[1] = rings[2] = 0;
+  rings[0] = rings[1] = rings[2] = rings[3] = 0;
   if (K % 32u || K / 32u < 2u) return false;
   const uint32_t min_ring = K / 32u + 1u;
-  for (int shape = 0; shape < 3; ++shape)
+  for (int shape = 0; shape < 4; ++shape)
     for (uint32_t ring = tc::RING_MAX; ring >= min_ring; --ring)
-      if (v4::smem_bytes(K, ring, shape == 2, shape == 0) <= (size_t)smem_max) { rings[shape] = ring; break; }
+      if (v4::smem_bytes(K, ring, shape == 2, shape == 0, shape == 3) <= (size_t)smem_max) { rings[shape] = ring; break; }
   return rings[0] || rings[1];
 }
 
@@ -860,13 +877,15 @@ cudaError_t launch_chain_v4(const ChainParams &p_in, cudaStream_t stream, int va
   ChainParams p = p_in;
   p.ablate = ((uint32_t)variant >> 4) & 3u;
   p.tc_sub = sub_for(p.tc_K);
-  const int shape = (int)p.tc_ff; // 0, 1, 2 as above
-  const size_t smem = smem_bytes(p.tc_K, p.tc_ring, shape == 2, shape == 0);
-  auto kern = shape == 2 ? chain_kernel<true, false> : shape == 0 ? chain_kernel<false, true> : chain_kernel<false, false>;
+  const int shape = (int)p.tc_ff; // 0..3 as above
+  const size_t smem = smem_bytes(p.tc_K, p.tc_ring, shape == 2, shape == 0, shape == 3);
+  auto kern = shape == 2 ? chain_kernel<true, false, false> : shape == 0 ? chain_kernel<false, true, false>
+            : shape == 3 ? chain_kernel<false, false, true> : chain_kernel<false, false, false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  if (info) { info->grid = (int)p.W; info->block = kThreads; info->smem = smem; info->tile = SPAN; }
-  kern<<<p.W, kThreads, smem, stream>>>(p);
+  const uint32_t grid = shape == 3 ? p.W / 2 : p.W; // p.W = chains per wave; the DUAL shape runs two per CTA
+  if (info) { info->grid = (int)grid; info->block = kThreads; info->smem = smem; info->tile = SPAN; }
+  kern<<<grid, kThreads, smem, stream>>>(p);
   return cudaGetLastError();
 }
 

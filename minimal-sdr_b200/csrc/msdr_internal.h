@@ -68,7 +68,7 @@ uint32_t chain_tile_samples();
 cudaError_t launch_chain_v4(const ChainParams &p, cudaStream_t stream, int variant, ChainLaunchInfo *info);
 uint32_t chain_v4_span_samples();
 uint32_t chain_v4_unit_samples();
-bool chain_v4_config(uint32_t K, int smem_max, uint32_t rings[3]);
+bool chain_v4_config(uint32_t K, int smem_max, uint32_t rings[4]);
 
 // stage-level kernels on device buffers
 cudaError_t launch_mix_fs4(const int16_t *in, int16_t *I, int16_t *Q, uint32_t rows, uint32_t n, size_t stride, cudaStream_t s);
