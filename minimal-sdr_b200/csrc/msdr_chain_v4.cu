@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
         }
       } else if (is_mma) {
         q += npairs;
-        if (lane == 0) {
+        { // warp-uniform: every lane waits, one elected lane issues (see umma_i8)
           uint32_t nt = ntile;
           for (uint32_t t = tb; t < te; ++t, ++nt) {
             const uint32_t qt = qbase + (t - tb) + KS - 1; // newest pair of this tile's window

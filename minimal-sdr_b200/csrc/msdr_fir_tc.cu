@@ -146,19 +146,18 @@ __global__ void __launch_bounds__(kThreads, 1) fir_demod_tc_kernel(const TcParam
       }
     } else if (is_mma) {
       q += npairs;
-      if (lane == 0) {
-        for (uint32_t t = tb; t < te; ++t, ++ntile) {
-          const uint32_t qt = qbase + (t - tb) + KS - 1; // newest pair of this tile's window
-          mbar_wait(&tc->a_full[qt % RING], (qt / RING) & 1u);
-          mbar_wait(&tc->tmem_empty, (ntile & 1u) ^ 1u);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          issue_tile(ictx, tmem, qt, KS, RING);
-          umma_commit(&tc->tmem_full);
-          umma_commit(&tc->blk_free[(qt - (KS - 1)) % RING]); // the oldest pair of the window is not read again
-        }
-        // the remaining pairs of the last window are free once the last MMAs have completed
-        for (uint32_t s = 1; s < KS; ++s) umma_commit(&tc->blk_free[(qbase + npairs - KS + s) % RING]);
+      // warp-uniform: every lane waits, one elected lane issues (see umma_i8)
+      for (uint32_t t = tb; t < te; ++t, ++ntile) {
+        const uint32_t qt = qbase + (t - tb) + KS - 1; // newest pair of this tile's window
+        mbar_wait(&tc->a_full[qt % RING], (qt / RING) & 1u);
+        mbar_wait(&tc->tmem_empty, (ntile & 1u) ^ 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        issue_tile(ictx, tmem, qt, KS, RING);
+        umma_commit(&tc->tmem_full);
+        umma_commit(&tc->blk_free[(qt - (KS - 1)) % RING]); // the oldest pair of the window is not read again
       }
+      // the remaining pairs of the last window are free once the last MMAs have completed
+      for (uint32_t s = 1; s < KS; ++s) umma_commit(&tc->blk_free[(qbase + npairs - KS + s) % RING]);
       __syncwarp();
     } else { // epilogue: thread = channel row (TMEM lane)
       q += npairs;

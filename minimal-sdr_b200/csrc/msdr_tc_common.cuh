@@ -30,9 +30,13 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= (uint64_t)1 << 46; // descriptor version (sm_100)
   return d;
 }
+// The MMA warp runs its loop warp-uniformly and ONE elected lane issues (elect.sync inside the asm): descriptors and TMEM
+// addresses are then warp-uniform values the compiler keeps in uniform registers.  Issued from inside `if (lane == 0)` every
+// operand goes through a R2UR broadcast loop (~100 cycles of single-thread latency per MMA).
 __device__ __forceinline__ void umma_commit(uint64_t *bar)
 {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+               "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_512(uint32_t *slot)
 {
@@ -86,8 +90,8 @@ __device__ __forceinline__ void umma_i8(uint32_t dcol, uint64_t da, uint64_t db,
 {
   const uint32_t idesc = (2u << 4) | (a_signed << 7) | (b_signed << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
   asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+      "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
       ::"r"(dcol), "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(0), "r"(0), "r"(0), "r"(0)
       : "memory");
 }
