@@ -212,6 +212,30 @@ int32_t msdr_amp_gain_multiplier(float gain);
  * Multiplier 65536 leaves the data unchanged and 0 gives zeros (the reference transmits no block at all for 0). */
 int msdr_op_amplifier(int device, const int32_t *multipliers, int16_t *data, uint32_t rows, uint32_t n, size_t stride);
 
+/* ---- LMS automatic notch / noise reduction: Minimal-SDR.ino:702-770 ------------------------------------------
+ * The sketch runs it on p_dac between demodulation and queue_dac when ANR_on > 0 (1 = notch: output the LMS error, 2 = noise
+ * reduction: output the prediction).  Stand-alone stateful operator on demodulated int16 audio [n_channels][stride], in place;
+ * 64 taps, 512-entry delay line, float32 with the reference's double sub-expressions; bit-exact with the reference compiled
+ * for the host.  Not fused into the receive chain kernel (whose biquads it would precede). */
+typedef struct msdr_anr msdr_anr;
+typedef struct msdr_anr_state {
+  float d[512];   /* ANR_d, .ino:724 */
+  float w[64];    /* ANR_w[0..63], .ino:725 */
+  float lidx;     /* .ino:715 */
+  float ngamma;   /* .ino:718 */
+  int32_t in_idx; /* .ino:723 */
+} msdr_anr_state;
+int msdr_anr_create(msdr_anr **out, int device, uint32_t n_channels);
+void msdr_anr_destroy(msdr_anr *anr);
+int msdr_anr_set_stream(msdr_anr *anr, void *cuda_stream);
+int msdr_anr_synchronize(msdr_anr *anr);
+const char *msdr_anr_last_error(const msdr_anr *anr);
+int msdr_anr_update(msdr_anr *anr, int mode, int16_t *data, uint32_t n_blocks, size_t stride);          /* host buffer, synchronous */
+int msdr_anr_update_device(msdr_anr *anr, int mode, int16_t *d_data, uint32_t n_blocks, size_t stride);  /* device buffer, asynchronous */
+int msdr_anr_get_state(msdr_anr *anr, uint32_t ch, msdr_anr_state *out);
+int msdr_anr_set_state(msdr_anr *anr, uint32_t ch, const msdr_anr_state *in);
+uint64_t msdr_anr_launch_count(const msdr_anr *anr);
+
 const char *msdr_version(void);
 
 #ifdef __cplusplus

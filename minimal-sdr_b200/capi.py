@@ -40,6 +40,10 @@ class FrontendState(C.Structure):  # msdr_frontend_state
     ]
 
 
+class AnrState(C.Structure):  # msdr_anr_state
+    _fields_ = [("d", C.c_float * 512), ("w", C.c_float * 64), ("lidx", C.c_float), ("ngamma", C.c_float), ("in_idx", C.c_int32)]
+
+
 def lib_path():
     return os.path.join(_HERE, "csrc", "libmsdr.so")
 
@@ -91,6 +95,16 @@ SYMBOLS = {
     "msdr_frontend_launch_count": (C.c_uint64, [C.c_void_p]),
     "msdr_amp_gain_multiplier": (C.c_int32, [C.c_float]),
     "msdr_op_amplifier": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_size_t]),
+    "msdr_anr_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_uint32]),
+    "msdr_anr_destroy": (None, [C.c_void_p]),
+    "msdr_anr_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "msdr_anr_synchronize": (C.c_int, [C.c_void_p]),
+    "msdr_anr_last_error": (C.c_char_p, [C.c_void_p]),
+    "msdr_anr_update": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_uint32, C.c_size_t]),
+    "msdr_anr_update_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_uint32, C.c_size_t]),
+    "msdr_anr_get_state": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(AnrState)]),
+    "msdr_anr_set_state": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(AnrState)]),
+    "msdr_anr_launch_count": (C.c_uint64, [C.c_void_p]),
     "msdr_version": (C.c_char_p, []),
 }
 

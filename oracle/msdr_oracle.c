@@ -528,3 +528,84 @@ void orc_frontend_run(orc_frontend *f, uint32_t n_channels, const uint16_t *adc,
     }
   }
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * LMS automatic notch / noise reduction: Minimal-SDR.ino:702-770, between the demodulator and the DAC
+ * queue (the biquads follow as audio objects).  Variable-leak LMS after Warren Pratt's wdsp.  float32_t state, with the
+ * `double` sub-expressions C's usual arithmetic conversions give the literals 1.0 and 1e-10.  Every operation below is a
+ * separately rounded IEEE operation in the order the source evaluates it (x86-64 gcc without -ffast-math does the same).
+ * ------------------------------------------------------------------------------------------------------------------ */
+#define ORC_ANR_DLINE 512 /* .ino:707 */
+#define ORC_ANR_TAPS 64   /* .ino:708 */
+#define ORC_ANR_DELAY 16  /* .ino:709 */
+
+typedef struct {
+  float d[ORC_ANR_DLINE]; /* .ino:724 */
+  float w[ORC_ANR_DLINE]; /* .ino:725 (only the first 64 are used) */
+  float lidx;             /* .ino:715: 120 */
+  float ngamma;           /* .ino:718: 0.001 */
+  int in_idx;             /* .ino:723 */
+} orc_anr;
+
+void orc_anr_init(orc_anr *a)
+{
+  memset(a, 0, sizeof(*a));
+  a->lidx = 120.0f;
+  a->ngamma = 0.001f;
+}
+
+/* mode 1: notch filter (output = error), mode 2: noise reduction (output = y)  (.ino:749-750) */
+void orc_anr_block(orc_anr *a, int mode, int16_t *p_dac, uint32_t n)
+{
+  const float two_mu = 0.001f, gamma = 0.1f, lidx_min = 0.0f, lidx_max = 200.0f, den_mult = 6.25e-10f, lincr = 1.0f, ldecr = 3.0f;
+  const int mask = ORC_ANR_DLINE - 1;
+  for (uint32_t i = 0; i < n; i++) {
+    a->d[a->in_idx] = p_dac[i];
+    float y = 0, sigma = 0;
+    for (int j = 0; j < ORC_ANR_TAPS; j++) {
+      const int idx = (a->in_idx + j + ORC_ANR_DELAY) & mask;
+      y += a->w[j] * a->d[idx];
+      sigma += a->d[idx] * a->d[idx];
+    }
+    const float inv_sigp = 1.0 / (sigma + 1e-10);
+    const float error = a->d[a->in_idx] - y;
+    if (mode == 1) p_dac[i] = error; else p_dac[i] = y;
+    float nel, nev;
+    if ((nel = error * (1.0 - two_mu * sigma * inv_sigp)) < 0.0) nel = -nel;
+    if ((nev = a->d[a->in_idx] - (1.0 - two_mu * a->ngamma) * y - two_mu * error * sigma * inv_sigp) < 0.0) nev = -nev;
+    if (nev < nel) {
+      if ((a->lidx += lincr) > lidx_max) a->lidx = lidx_max;
+      else if ((a->lidx -= ldecr) < lidx_min) a->lidx = lidx_min;
+    }
+    a->ngamma = gamma * (a->lidx * a->lidx) * (a->lidx * a->lidx) * den_mult;
+    const float c0 = 1.0 - two_mu * a->ngamma;
+    const float c1 = two_mu * error * inv_sigp;
+    for (int j = 0; j < ORC_ANR_TAPS; j++) {
+      const int idx = (a->in_idx + j + ORC_ANR_DELAY) & mask;
+      a->w[j] = c0 * a->w[j] + c1 * a->d[idx];
+    }
+    a->in_idx = (a->in_idx + mask) & mask;
+  }
+}
+
+orc_anr *orc_anr_new(uint32_t n_channels)
+{
+  orc_anr *a = (orc_anr *)malloc((n_channels ? n_channels : 1) * sizeof(orc_anr));
+  for (uint32_t i = 0; a && i < n_channels; i++) orc_anr_init(&a[i]);
+  return a;
+}
+void orc_anr_free(orc_anr *a) { free(a); }
+void orc_anr_run(orc_anr *a, uint32_t n_channels, int mode, int16_t *data, uint32_t n_blocks, size_t stride)
+{
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+  for (long c = 0; c < (long)n_channels; c++)
+    for (uint32_t b = 0; b < n_blocks; b++) orc_anr_block(&a[c], mode, data + (size_t)c * stride + (size_t)b * ORC_BLOCK, ORC_BLOCK);
+}
+void orc_anr_get(const orc_anr *a, uint32_t ch, float *lidx, float *ngamma, int *in_idx, float *w64, float *d512)
+{
+  *lidx = a[ch].lidx; *ngamma = a[ch].ngamma; *in_idx = a[ch].in_idx;
+  memcpy(w64, a[ch].w, ORC_ANR_TAPS * sizeof(float));
+  memcpy(d512, a[ch].d, ORC_ANR_DLINE * sizeof(float));
+}

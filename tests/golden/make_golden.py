@@ -112,6 +112,14 @@ def main():
     fe["agc_blocks"] = ablocks
     fe["agc_val"], fe["agc_mult"] = fl.Ref.agc_trajectory(ablocks, 0.25, 40.0)
     np.savez_compressed(os.path.join(HERE, "frontend_kat.npz"), **fe)
+
+    # LMS notch / noise reduction: the reference's own block, one stream per fresh process
+    import anr_lib as al
+    ax = al.audio_stream(2, 128 * 30, seed=31)
+    anr = {"x": ax}
+    for mode in (1, 2):
+        anr[f"y_mode{mode}"] = np.stack([al.ref_anr_run(mode, ax[c]) for c in range(2)])
+    np.savez_compressed(os.path.join(HERE, "anr_kat.npz"), **anr)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
