@@ -236,6 +236,23 @@ int msdr_anr_get_state(msdr_anr *anr, uint32_t ch, msdr_anr_state *out);
 int msdr_anr_set_state(msdr_anr *anr, uint32_t ch, const msdr_anr_state *in);
 uint64_t msdr_anr_launch_count(const msdr_anr *anr);
 
+/* ---- synchronous-AM demodulator with PLL: `case SYNCAM`, Minimal-SDR.ino:631-688 -------------------------------
+ * Stand-alone stateful operator: the FIR-filtered I and Q streams [n_channels][stride] in, corr[0] narrowed to int16 out.
+ * float32 with transcendental functions; parity with the reference compiled for a host is a tolerance (libm implementations
+ * differ in the last ulp): <= 1e-5 relative RMS, tests/test_gpu_syncam.py.  The fused chain kernel does not run this mode
+ * (msdr_chain_set_mode(SYNCAM) without MSDR_FLAG_AM_Q31 returns MSDR_ERR_UNSUPPORTED). */
+typedef struct msdr_syncam msdr_syncam;
+int msdr_syncam_create(msdr_syncam **out, int device, uint32_t n_channels);
+void msdr_syncam_destroy(msdr_syncam *sc);
+int msdr_syncam_set_stream(msdr_syncam *sc, void *cuda_stream);
+const char *msdr_syncam_last_error(const msdr_syncam *sc);
+int msdr_syncam_update(msdr_syncam *sc, const int16_t *I, const int16_t *Q, int16_t *out, uint32_t n_blocks, size_t stride);
+int msdr_syncam_update_device(msdr_syncam *sc, const int16_t *d_I, const int16_t *d_Q, int16_t *d_out, uint32_t n_blocks, size_t stride);
+int msdr_syncam_get_state(msdr_syncam *sc, uint32_t ch, float *fil_out, float *omega2, float *phzerror);
+int msdr_syncam_set_state(msdr_syncam *sc, uint32_t ch, float fil_out, float omega2, float phzerror);
+int msdr_syncam_constants(float *omega_min, float *omega_max, float *g1, float *g2);
+uint64_t msdr_syncam_launch_count(const msdr_syncam *sc);
+
 const char *msdr_version(void);
 
 #ifdef __cplusplus

@@ -105,6 +105,16 @@ SYMBOLS = {
     "msdr_anr_get_state": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(AnrState)]),
     "msdr_anr_set_state": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(AnrState)]),
     "msdr_anr_launch_count": (C.c_uint64, [C.c_void_p]),
+    "msdr_syncam_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_uint32]),
+    "msdr_syncam_destroy": (None, [C.c_void_p]),
+    "msdr_syncam_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "msdr_syncam_last_error": (C.c_char_p, [C.c_void_p]),
+    "msdr_syncam_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_size_t]),
+    "msdr_syncam_update_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_size_t]),
+    "msdr_syncam_get_state": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "msdr_syncam_set_state": (C.c_int, [C.c_void_p, C.c_uint32, C.c_float, C.c_float, C.c_float]),
+    "msdr_syncam_constants": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "msdr_syncam_launch_count": (C.c_uint64, [C.c_void_p]),
     "msdr_version": (C.c_char_p, []),
 }
 

@@ -609,3 +609,68 @@ void orc_anr_get(const orc_anr *a, uint32_t ch, float *lidx, float *ngamma, int 
   memcpy(w64, a[ch].w, ORC_ANR_TAPS * sizeof(float));
   memcpy(d512, a[ch].d, ORC_ANR_DLINE * sizeof(float));
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Synchronous AM demodulator with PLL: `case SYNCAM` of the demodulation switch, Minimal-SDR.ino:631-688
+ * (Teensy 3.5/3.6 branch; after wdsp).  Input: the FIR-filtered I and Q blocks; output: corr[0] narrowed to int16.
+ * float32 with libm sinf/cosf/atan2f, `double` where the literals 2.0 * PI force it.  Restated operation by operation; the
+ * constants are evaluated with the same expressions as the sketch's static initialisers (SAMPLE_RATE = 24000, .ino:84-85).
+ * ------------------------------------------------------------------------------------------------------------------ */
+#define ORC_PI 3.1415926535897932384626433832795 /* Arduino.h PI */
+#define ORC_SAMPLE_RATE (6000 * 4)
+
+typedef struct {
+  float fil_out, omega2, phzerror; /* .ino:643-645 */
+} orc_syncam;
+
+void orc_syncam_constants(float *omega_min, float *omega_max, float *g1, float *g2)
+{
+  const float omegaN = 400.0, zeta = 0.45;
+  *omega_min = 2.0 * ORC_PI * -4000.0 / ORC_SAMPLE_RATE;
+  *omega_max = 2.0 * ORC_PI * 4000.0 / ORC_SAMPLE_RATE;
+  const float g1v = 1.0 - exp(-2.0 * omegaN * zeta / ORC_SAMPLE_RATE);
+  *g1 = g1v;
+  /* the sketch is C++: exp() of a float argument is the float overload, and `1 - float * float` stays float */
+  *g2 = -g1v + 2.0 * (1 - expf(-omegaN * zeta / ORC_SAMPLE_RATE) * cosf(omegaN / ORC_SAMPLE_RATE * sqrtf(1.0 - zeta * zeta)));
+}
+
+void orc_syncam_block(orc_syncam *s, const int16_t *I_buffer, const int16_t *Q_buffer, int16_t *p_dac, uint32_t n)
+{
+  float omega_min, omega_max, g1, g2;
+  orc_syncam_constants(&omega_min, &omega_max, &g1, &g2);
+  for (uint32_t i = 0; i < n; i++) {
+    const float Sin = sinf(s->phzerror), Cos = cosf(s->phzerror);
+    const float ai = Cos * I_buffer[i], bi = Sin * I_buffer[i], aq = Cos * Q_buffer[i], bq = Sin * Q_buffer[i];
+    float corr[2];
+    corr[0] = +ai + bq;
+    corr[1] = -bi + aq;
+    p_dac[i] = corr[0];
+    const float det = atan2f(corr[1], corr[0]);
+    const float del_out = s->fil_out;
+    s->omega2 = s->omega2 + g2 * det;
+    if (s->omega2 < omega_min) s->omega2 = omega_min;
+    else if (s->omega2 > omega_max) s->omega2 = omega_max;
+    s->fil_out = g1 * det + s->omega2;
+    s->phzerror = s->phzerror + del_out;
+    while (s->phzerror >= 2 * ORC_PI) s->phzerror -= 2.0 * ORC_PI;
+    while (s->phzerror < 0.0) s->phzerror += 2.0 * ORC_PI;
+  }
+}
+
+orc_syncam *orc_syncam_new(uint32_t n_channels) { return (orc_syncam *)calloc(n_channels ? n_channels : 1, sizeof(orc_syncam)); }
+void orc_syncam_free(orc_syncam *s) { free(s); }
+void orc_syncam_run(orc_syncam *s, uint32_t n_channels, const int16_t *I, const int16_t *Q, int16_t *out, uint32_t n_blocks, size_t stride)
+{
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+  for (long c = 0; c < (long)n_channels; c++)
+    for (uint32_t b = 0; b < n_blocks; b++) {
+      const size_t off = (size_t)c * stride + (size_t)b * ORC_BLOCK;
+      orc_syncam_block(&s[c], I + off, Q + off, out + off, ORC_BLOCK);
+    }
+}
+void orc_syncam_get(const orc_syncam *s, uint32_t ch, float *fil_out, float *omega2, float *phzerror)
+{
+  *fil_out = s[ch].fil_out; *omega2 = s[ch].omega2; *phzerror = s[ch].phzerror;
+}

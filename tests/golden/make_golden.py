@@ -120,6 +120,11 @@ def main():
     for mode in (1, 2):
         anr[f"y_mode{mode}"] = np.stack([al.ref_anr_run(mode, ax[c]) for c in range(2)])
     np.savez_compressed(os.path.join(HERE, "anr_kat.npz"), **anr)
+
+    # synchronous-AM PLL: the reference's own `case SYNCAM` arm, one stream per fresh process
+    import syncam_lib as sl
+    sI, sQ = sl.baseband(2, 128 * 40, seed=41)
+    np.savez_compressed(os.path.join(HERE, "syncam_kat.npz"), I=sI, Q=sQ, y=np.stack([sl.ref_syncam_run(sI[c], sQ[c]) for c in range(2)]))
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
