@@ -63,6 +63,7 @@ typedef struct {
                                                    the reference's two pState delay lines (arm_fir_fast_q15.c:296-327) are
                                                    this sequence after the fs/4 mix */
   int32_t biquad_definition[MSDR_BIQUAD_OBJECTS][32]; /* filter_biquad.h:152 layout, verbatim */
+  float syncam_pll[3];                          /* fil_out, omega2, phzerror of the SYNCAM PLL (Minimal-SDR.ino:643-645) */
 } msdr_channel_state;
 
 /* ---- lifetime -------------------------------------------------------------------------------- */
@@ -239,8 +240,8 @@ uint64_t msdr_anr_launch_count(const msdr_anr *anr);
 /* ---- synchronous-AM demodulator with PLL: `case SYNCAM`, Minimal-SDR.ino:631-688 -------------------------------
  * Stand-alone stateful operator: the FIR-filtered I and Q streams [n_channels][stride] in, corr[0] narrowed to int16 out.
  * float32 with transcendental functions; parity with the reference compiled for a host is a tolerance (libm implementations
- * differ in the last ulp): <= 1e-5 relative RMS, tests/test_gpu_syncam.py.  The fused chain kernel does not run this mode
- * (msdr_chain_set_mode(SYNCAM) without MSDR_FLAG_AM_Q31 returns MSDR_ERR_UNSUPPORTED). */
+ * differ in the last ulp): <= 1e-5 relative RMS, tests/test_gpu_syncam.py.  A receive chain runs this operator for its channels
+ * in mode SYNCAM (without MSDR_FLAG_AM_Q31) beside the fused kernel, on scratch copies of those channels (msdr_capi.cu). */
 typedef struct msdr_syncam msdr_syncam;
 int msdr_syncam_create(msdr_syncam **out, int device, uint32_t n_channels);
 void msdr_syncam_destroy(msdr_syncam *sc);

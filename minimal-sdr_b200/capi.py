@@ -25,6 +25,7 @@ class ChannelState(C.Structure):
         ("fir_set", C.c_int32),
         ("fir_history", C.c_int16 * MAX_TAPS),
         ("biquad_definition", (C.c_int32 * 32) * 2),
+        ("syncam_pll", C.c_float * 3),
     ]
 
 

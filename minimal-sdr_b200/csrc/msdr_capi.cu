@@ -102,6 +102,17 @@ struct msdr_chain {
   int *d_tile_cnt = nullptr;
   size_t tile_cnt_len = 0;
 
+  // mode SYNCAM with the f32 PLL (.ino:631-688): a serial loop through sinf/cosf/atan2f per channel, run beside the fused kernel
+  // on dense scratch copies of those channels (see syncam_lane_*)
+  float *d_pll = nullptr;            // [3][Cpad] fil_out, omega2, phzerror
+  struct PllLane {
+    std::vector<uint32_t> rows;      // launch-relative rows, ordered by tap table
+    uint32_t *d_rows = nullptr, *d_chmap = nullptr;
+    int16_t *d_raw = nullptr, *d_I = nullptr, *d_Q = nullptr, *d_If = nullptr, *d_Qf = nullptr, *d_taps = nullptr;
+    int32_t *d_defs = nullptr;
+    size_t cap_rows = 0, cap_samples = 0;
+  } pll;
+
   int variant = 0;
   uint32_t host_chunk_channels = 0, host_chunk_blocks = 0; // 0 = auto
   uint64_t launches = 0;
@@ -244,6 +255,8 @@ int msdr_chain_create(msdr_chain **out, int device, uint32_t n_channels, uint32_
   CKC(cudaMalloc(&chain->d_set, n_channels));
   CKC(cudaMalloc(&chain->d_hist, (size_t)n_channels * chain->H * sizeof(int16_t)));
   CKC(cudaMalloc(&chain->d_bq, (size_t)kBqWords * chain->Cpad * sizeof(int32_t)));
+  CKC(cudaMalloc(&chain->d_pll, (size_t)3 * chain->Cpad * sizeof(float)));
+  CKC(cudaMemset(chain->d_pll, 0, (size_t)3 * chain->Cpad * sizeof(float)));
   CKC(cudaMalloc(&chain->d_sets, (size_t)MSDR_MAX_FIR_SETS * chain->set_stride_words * sizeof(int32_t)));
   CKC(cudaMalloc(&chain->d_set_kp4, MSDR_MAX_FIR_SETS * sizeof(uint32_t)));
   CKC(cudaMalloc(&chain->d_ctrl, (size_t)(1 + chain->Cpad / kGroup + 1) * sizeof(int)));
@@ -266,7 +279,9 @@ void msdr_chain_destroy(msdr_chain *chain)
   if (chain->stream) cudaStreamSynchronize(chain->stream);
   cudaFree(chain->d_mode); cudaFree(chain->d_set); cudaFree(chain->d_hist); cudaFree(chain->d_bq);
   cudaFree(chain->plan.d_rowmap); cudaFree(chain->plan.d_grp); cudaFree(chain->plan.d_wave_rb0); cudaFree(chain->plan.d_rb); cudaFree(chain->plan.d_bmat);
-  cudaFree(chain->d_tile_cnt);
+  cudaFree(chain->d_tile_cnt); cudaFree(chain->d_pll);
+  cudaFree(chain->pll.d_rows); cudaFree(chain->pll.d_chmap); cudaFree(chain->pll.d_raw); cudaFree(chain->pll.d_I); cudaFree(chain->pll.d_Q);
+  cudaFree(chain->pll.d_If); cudaFree(chain->pll.d_Qf); cudaFree(chain->pll.d_taps); cudaFree(chain->pll.d_defs);
   cudaFree(chain->d_sets); cudaFree(chain->d_set_kp4); cudaFree(chain->d_ctrl); cudaFree(chain->d_tile_flags);
   cudaFree(chain->d_in); cudaFree(chain->d_out);
   if (chain->pin_in) cudaFreeHost(chain->pin_in);
@@ -305,8 +320,6 @@ int msdr_chain_set_mode(msdr_chain *chain, uint32_t ch0, uint32_t nch, int mode)
 {
   if (!chain) return MSDR_ERR_ARGUMENT;
   if (!range_ok(chain, ch0, nch) || mode < 0 || mode > 4) return fail(chain, MSDR_ERR_ARGUMENT, "set_mode: bad channel range or mode");
-  if (mode == MSDR_MODE_SYNCAM && !(chain->flags & MSDR_FLAG_AM_Q31))
-    return fail(chain, MSDR_ERR_UNSUPPORTED, "SYNCAM PLL demodulator (Minimal-SDR.ino:631-688) is not on the hot path; use MSDR_FLAG_AM_Q31 for the Teensy 3.2 envelope");
   if (nch == 0) return MSDR_OK;
   CK(cudaSetDevice(chain->device));
   std::fill(chain->h_mode.begin() + ch0, chain->h_mode.begin() + ch0 + nch, (uint8_t)mode);
@@ -444,6 +457,81 @@ int build_tc_plan(msdr_chain *chain, uint32_t ch0, uint32_t nch, uint32_t W)
 
 } // namespace
 
+namespace {
+
+// ---- channels in mode SYNCAM without MSDR_FLAG_AM_Q31: the f32 PLL demodulator (Minimal-SDR.ino:631-688) -------------------------
+// The fused kernel has no serial PLL stage.  It processes these channels like any other (their result is thrown away); their
+// real result is computed on dense scratch copies with the stage kernels and written over it:
+//   before the fused kernel   gather  hist || in  rows and the biquad words of both objects
+//   after it                  fs/4 mix -> FIR pair (zero initial state over hist || in: exact from sample 0 on, H >= taps - 1)
+//                             -> PLL (state per chain channel) -> biquad object 1, 2 -> scatter audio and biquad words back
+// The raw-sample history is the fused kernel's to update; it is correct for every channel.
+int syncam_lane_prepare(msdr_chain *chain, uint32_t ch0, uint32_t nch, const int16_t *d_in, size_t stride, uint32_t L)
+{
+  msdr_chain::PllLane &ln = chain->pll;
+  ln.rows.clear();
+  if (chain->flags & MSDR_FLAG_AM_Q31) return MSDR_OK; // Teensy 3.2 arithmetic: SYNCAM is the q31 envelope (.ino:618-620)
+  for (uint32_t r = 0; r < nch; ++r)
+    if (chain->h_mode[ch0 + r] == MSDR_MODE_SYNCAM) ln.rows.push_back(r);
+  if (ln.rows.empty()) return MSDR_OK;
+  std::stable_sort(ln.rows.begin(), ln.rows.end(), [&](uint32_t a, uint32_t b) { return chain->h_set[ch0 + a] < chain->h_set[ch0 + b]; });
+  const uint32_t n = (uint32_t)ln.rows.size();
+  const size_t Lp = (size_t)chain->H + L, samples = (size_t)n * Lp;
+  if (n > ln.cap_rows || samples > ln.cap_samples) {
+    CK(cudaStreamSynchronize(chain->stream));
+    cudaFree(ln.d_rows); cudaFree(ln.d_chmap); cudaFree(ln.d_raw); cudaFree(ln.d_I); cudaFree(ln.d_Q); cudaFree(ln.d_If); cudaFree(ln.d_Qf); cudaFree(ln.d_taps);
+    cudaFree(ln.d_defs);
+    ln.d_rows = ln.d_chmap = nullptr; ln.d_raw = ln.d_I = ln.d_Q = ln.d_If = ln.d_Qf = ln.d_taps = nullptr; ln.d_defs = nullptr;
+    ln.cap_rows = ln.cap_samples = 0;
+    CK(cudaMalloc(&ln.d_rows, n * 4)); CK(cudaMalloc(&ln.d_chmap, n * 4)); CK(cudaMalloc(&ln.d_defs, (size_t)n * 64 * 4));
+    CK(cudaMalloc(&ln.d_taps, 2 * MSDR_MAX_TAPS * sizeof(int16_t)));
+    CK(cudaMalloc(&ln.d_raw, samples * 2)); CK(cudaMalloc(&ln.d_I, samples * 2)); CK(cudaMalloc(&ln.d_Q, samples * 2));
+    CK(cudaMalloc(&ln.d_If, samples * 2)); CK(cudaMalloc(&ln.d_Qf, samples * 2));
+    ln.cap_rows = n; ln.cap_samples = samples;
+  }
+  std::vector<uint32_t> chmap(n);
+  for (uint32_t i = 0; i < n; ++i) chmap[i] = ch0 + ln.rows[i];
+  CK(cudaMemcpyAsync(ln.d_rows, ln.rows.data(), n * 4, cudaMemcpyHostToDevice, chain->stream));
+  CK(cudaMemcpyAsync(ln.d_chmap, chmap.data(), n * 4, cudaMemcpyHostToDevice, chain->stream));
+  CK(cudaStreamSynchronize(chain->stream)); // the index vectors are temporaries / reused host storage
+  CK(launch_gather_rows(ln.d_rows, n, ch0, chain->d_hist, chain->H, d_in, stride, ln.d_raw, L, chain->stream));
+  CK(launch_bq_words(0, ln.d_rows, n, ch0, chain->d_bq, chain->Cpad, ln.d_defs, chain->stream));
+  chain->launches += 2;
+  return MSDR_OK;
+}
+
+int syncam_lane_finish(msdr_chain *chain, uint32_t ch0, int16_t *d_out, size_t stride, uint32_t L)
+{
+  msdr_chain::PllLane &ln = chain->pll;
+  if (ln.rows.empty()) return MSDR_OK;
+  const uint32_t n = (uint32_t)ln.rows.size(), H = chain->H;
+  const size_t Lp = (size_t)H + L;
+  CK(launch_mix_fs4(ln.d_raw, ln.d_I, ln.d_Q, n, (uint32_t)Lp, Lp, chain->stream));
+  for (uint32_t i0 = 0; i0 < n;) { // one FIR launch pair per run of channels sharing a tap table
+    const uint8_t sid = chain->h_set[ch0 + ln.rows[i0]];
+    uint32_t i1 = i0;
+    while (i1 < n && chain->h_set[ch0 + ln.rows[i1]] == sid) ++i1;
+    const FirSet &fs = chain->sets[sid];
+    CK(cudaMemcpyAsync(ln.d_taps, fs.cI.data(), fs.T * 2, cudaMemcpyHostToDevice, chain->stream));
+    CK(cudaMemcpyAsync(ln.d_taps + MSDR_MAX_TAPS, fs.cQ.data(), fs.T * 2, cudaMemcpyHostToDevice, chain->stream));
+    CK(launch_fir_fast_q15(fs.T, ln.d_taps, nullptr, nullptr, ln.d_I + i0 * Lp, ln.d_If + i0 * Lp, i1 - i0, (uint32_t)Lp, Lp, chain->stream));
+    CK(launch_fir_fast_q15(fs.T, ln.d_taps + MSDR_MAX_TAPS, nullptr, nullptr, ln.d_Q + i0 * Lp, ln.d_Qf + i0 * Lp, i1 - i0, (uint32_t)Lp, Lp, chain->stream));
+    CK(cudaStreamSynchronize(chain->stream)); // d_taps is reused by the next table
+    chain->launches += 2;
+    i0 = i1;
+  }
+  int16_t *audio = ln.d_I; // reuse: [n][Lp], audio in the first L samples of every row
+  CK(launch_syncam(ln.d_If + H, ln.d_Qf + H, Lp, audio, Lp, n, L, chain->d_pll, chain->Cpad, ln.d_chmap, chain->stream));
+  CK(launch_biquad(ln.d_defs, audio, n, L, Lp, chain->stream));
+  CK(launch_biquad(ln.d_defs + (size_t)n * 32, audio, n, L, Lp, chain->stream));
+  CK(launch_scatter_rows(ln.d_rows, n, audio, Lp, d_out, stride, L, chain->stream));
+  CK(launch_bq_words(1, ln.d_rows, n, ch0, chain->d_bq, chain->Cpad, ln.d_defs, chain->stream));
+  chain->launches += 6;
+  return MSDR_OK;
+}
+
+} // namespace
+
 int msdr_chain_update_range_device(msdr_chain *chain, uint32_t ch0, uint32_t nch, const int16_t *d_in, int16_t *d_out, uint32_t n_blocks,
                                    size_t stride)
 {
@@ -524,6 +612,10 @@ int msdr_chain_update_range_device(msdr_chain *chain, uint32_t ch0, uint32_t nch
     }
   }
   if (chain->timed) CK(cudaEventRecord(chain->ev0, chain->stream));
+  {
+    int stl = syncam_lane_prepare(chain, ch0, nch, d_in, stride, p.L);
+    if (stl != MSDR_OK) return stl;
+  }
   static const bool prof_on = getenv("MSDR_PROF") != nullptr; // developer aid: per-role cycle totals of the v4 kernel on stderr
   long long *d_prof = nullptr;
   if (use_tc && prof_on) {
@@ -533,6 +625,10 @@ int msdr_chain_update_range_device(msdr_chain *chain, uint32_t ch0, uint32_t nch
   }
   if (use_tc) CK(launch_chain_v4(p, chain->stream, chain->variant, &chain->last_info));
   else CK(launch_chain(p, chain->stream, chain->variant, &chain->last_info));
+  {
+    int stl = syncam_lane_finish(chain, ch0, d_out, stride, p.L);
+    if (stl != MSDR_OK) return stl;
+  }
   if (chain->timed) CK(cudaEventRecord(chain->ev1, chain->stream));
   chain->launches++;
   if (d_prof) {
@@ -655,6 +751,7 @@ int msdr_chain_get_state(msdr_chain *chain, uint32_t ch, msdr_channel_state *out
   int32_t bq[kBqWords];
   CK(cudaMemcpy2D(bq, sizeof(int32_t), chain->d_bq + ch, (size_t)chain->Cpad * sizeof(int32_t), sizeof(int32_t), kBqWords, cudaMemcpyDeviceToHost));
   memcpy(out->biquad_definition, bq, sizeof(bq));
+  CK(cudaMemcpy2D(out->syncam_pll, sizeof(float), chain->d_pll + ch, (size_t)chain->Cpad * sizeof(float), sizeof(float), 3, cudaMemcpyDeviceToHost));
   return MSDR_OK;
 }
 
@@ -675,6 +772,7 @@ int msdr_chain_set_state(msdr_chain *chain, uint32_t ch, const msdr_channel_stat
   CK(cudaMemcpy(chain->d_hist + (size_t)ch * chain->H, h.data(), chain->H * sizeof(int16_t), cudaMemcpyHostToDevice));
   CK(cudaMemcpy2D(chain->d_bq + ch, (size_t)chain->Cpad * sizeof(int32_t), in->biquad_definition, sizeof(int32_t), sizeof(int32_t), kBqWords,
                   cudaMemcpyHostToDevice));
+  CK(cudaMemcpy2D(chain->d_pll + ch, (size_t)chain->Cpad * sizeof(float), in->syncam_pll, sizeof(float), sizeof(float), 3, cudaMemcpyHostToDevice));
   return MSDR_OK;
 }
 

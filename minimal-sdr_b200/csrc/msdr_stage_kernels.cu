@@ -283,4 +283,52 @@ cudaError_t launch_sqrt_check(unsigned long long *d_mismatch, cudaStream_t s)
   return cudaGetLastError();
 }
 
+
+// ---- glue for channels the fused kernel does not demodulate itself (mode SYNCAM with the f32 PLL): rows and biquad words are
+// copied out to dense scratch arrays, run through the stage kernels, and copied back (msdr_capi.cu)
+__global__ void gather_rows_kernel(const uint32_t *__restrict__ rows, uint32_t ch0, const int16_t *__restrict__ hist, uint32_t H,
+                                   const int16_t *__restrict__ in, size_t stride, int16_t *__restrict__ raw, uint32_t L)
+{
+  const uint32_t s = blockIdx.y, row = rows[s];
+  const size_t Lp = (size_t)H + L;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < Lp; i += (size_t)gridDim.x * blockDim.x)
+    raw[s * Lp + i] = i < H ? hist[((size_t)ch0 + row) * H + i] : in[(size_t)row * stride + (i - H)];
+}
+__global__ void scatter_rows_kernel(const uint32_t *__restrict__ rows, const int16_t *__restrict__ audio, size_t astride, int16_t *__restrict__ out,
+                                    size_t stride, uint32_t L)
+{
+  const uint32_t s = blockIdx.y, row = rows[s];
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < L; i += (size_t)gridDim.x * blockDim.x)
+    out[(size_t)row * stride + i] = audio[s * astride + i];
+}
+// d_bq is [2 objects * 4 stages * 8 words][Cpad]; defs is [object][n][32]
+__global__ void bq_words_kernel(int dir, const uint32_t *__restrict__ rows, uint32_t ch0, int32_t *__restrict__ bq, uint32_t Cpad, int32_t *__restrict__ defs, uint32_t n)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * 64u) return;
+  const uint32_t s = i / 64u, w = i % 64u; // w = object * 32 + word
+  int32_t *g = bq + (size_t)w * Cpad + ch0 + rows[s];
+  int32_t *d = defs + ((size_t)(w / 32u) * n + s) * 32u + (w % 32u);
+  if (dir == 0) *d = *g; else *g = *d;
+}
+cudaError_t launch_gather_rows(const uint32_t *rows, uint32_t n, uint32_t ch0, const int16_t *hist, uint32_t H, const int16_t *in, size_t stride, int16_t *raw,
+                               uint32_t L, cudaStream_t s)
+{
+  if (n == 0) return cudaSuccess;
+  gather_rows_kernel<<<dim3(8, n), 256, 0, s>>>(rows, ch0, hist, H, in, stride, raw, L);
+  return cudaGetLastError();
+}
+cudaError_t launch_scatter_rows(const uint32_t *rows, uint32_t n, const int16_t *audio, size_t astride, int16_t *out, size_t stride, uint32_t L, cudaStream_t s)
+{
+  if (n == 0) return cudaSuccess;
+  scatter_rows_kernel<<<dim3(8, n), 256, 0, s>>>(rows, audio, astride, out, stride, L);
+  return cudaGetLastError();
+}
+cudaError_t launch_bq_words(int dir, const uint32_t *rows, uint32_t n, uint32_t ch0, int32_t *bq, uint32_t Cpad, int32_t *defs, cudaStream_t s)
+{
+  if (n == 0) return cudaSuccess;
+  bq_words_kernel<<<(n * 64u + 255u) / 256u, 256, 0, s>>>(dir, rows, ch0, bq, Cpad, defs, n);
+  return cudaGetLastError();
+}
+
 } // namespace msdr

@@ -256,7 +256,10 @@ typedef struct {
   int mode;
   orc_fir *fir_i, *fir_q;
   orc_biquad bq[2];
+  float pll[3]; /* SYNCAM PLL: fil_out, omega2, phzerror (.ino:643-645) */
 } orc_channel;
+/* `case SYNCAM` on the Teensy 3.5/3.6 (f32 PLL, .ino:631-688); defined with the other next-row restatements below */
+void orc_syncam_block3(float *state3, const int16_t *I_buffer, const int16_t *Q_buffer, int16_t *p_dac, uint32_t n);
 
 typedef struct {
   uint32_t n_channels;
@@ -348,7 +351,8 @@ int orc_chain_run(orc_chain *c, const int16_t *in, int16_t *out, uint32_t n_bloc
       orc_mix_fs4(p_adc, I, Q, ORC_BLOCK);
       orc_fir_run(k->fir_i, I, If, ORC_BLOCK);
       orc_fir_run(k->fir_q, Q, Qf, ORC_BLOCK);
-      orc_demod(kind, If, Qf, p_dac, ORC_BLOCK);
+      if (k->mode == ORC_SYNCAM && !c->am_q31) orc_syncam_block3(k->pll, If, Qf, p_dac, ORC_BLOCK);
+      else orc_demod(kind, If, Qf, p_dac, ORC_BLOCK);
       orc_biquad_update(&k->bq[0], p_dac, ORC_BLOCK);
       orc_biquad_update(&k->bq[1], p_dac, ORC_BLOCK);
     }
@@ -655,6 +659,13 @@ void orc_syncam_block(orc_syncam *s, const int16_t *I_buffer, const int16_t *Q_b
     while (s->phzerror >= 2 * ORC_PI) s->phzerror -= 2.0 * ORC_PI;
     while (s->phzerror < 0.0) s->phzerror += 2.0 * ORC_PI;
   }
+}
+
+void orc_syncam_block3(float *state3, const int16_t *I_buffer, const int16_t *Q_buffer, int16_t *p_dac, uint32_t n)
+{
+  orc_syncam s = {state3[0], state3[1], state3[2]};
+  orc_syncam_block(&s, I_buffer, Q_buffer, p_dac, n);
+  state3[0] = s.fil_out; state3[1] = s.omega2; state3[2] = s.phzerror;
 }
 
 orc_syncam *orc_syncam_new(uint32_t n_channels) { return (orc_syncam *)calloc(n_channels ? n_channels : 1, sizeof(orc_syncam)); }

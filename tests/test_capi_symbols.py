@@ -32,7 +32,7 @@ def test_library_is_in_tree_and_native(msdr):
 
 
 def test_channel_state_layout(msdr):
-    assert C.sizeof(msdr.capi.ChannelState) == 4 + 4 + 4 + 2 * 256 + 4 * 64
+    assert C.sizeof(msdr.capi.ChannelState) == 4 + 4 + 4 + 2 * 256 + 4 * 64 + 4 * 3
 
 
 def test_no_cpu_fallback(msdr):

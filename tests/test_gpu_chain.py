@@ -193,9 +193,6 @@ def test_errors_match_reference_conventions(msdr, K):
         g.fir_init(np.zeros(104, np.int16), np.zeros(104, np.int16))  # longer than this chain's max_taps (102)
     with pytest.raises(msdr.MsdrError):
         g.set_mode(7)
-    with pytest.raises(msdr.MsdrError) as e:
-        g.set_mode(SYNCAM)                              # f32 build: PLL demodulator not on the hot path
-    assert e.value.status == msdr.capi.ERR_UNSUPPORTED
     g.fir_init(am, am)
     g.biquad_set_coefficients(0, 7, K["biquad1_lowpass_coef"])  # stage >= 4: silently ignored
     assert not g.update(x).any()
@@ -321,3 +318,32 @@ def test_every_kernel_shape_is_bit_exact(msdr, orc, K, variant, name):
     assert o.fir_init(7, 2, cI, cQ) == 0
     yg, yo = run_pair(g, o, x, splits=[3, 1, 17, 2, 18])
     assert_same(yg, yo, name)
+
+
+def test_syncam_channels_in_a_chain(msdr, orc, K):
+    """Mode SYNCAM on the f32 build = the PLL demodulator (Minimal-SDR.ino:631-688), run beside the fused kernel for those channels.
+    Every other channel stays bit-exact; SYNCAM channels meet the float tolerance (libm-dependent path) after both biquads, with
+    FIR history, PLL state and biquad state carried over ragged updates and across a migration to another chain."""
+    modes = msdr.synth.mixed_modes(70)
+    pll = [3, 4, 5, 40, 64, 69]
+    for c in pll:
+        modes[c] = SYNCAM
+    x = msdr.synth.batch(modes, 128 * 60)
+    g, o = configure_pair(msdr, orc, K, modes)
+    yo = o.run(x)[0]
+    outs, b0 = [], 0
+    for n in (1, 7, 22):
+        outs.append(g.update(np.ascontiguousarray(x[:, b0 * 128:(b0 + n) * 128])))
+        b0 += n
+    g2, _ = configure_pair(msdr, orc, K, modes)  # migrate every channel to a fresh chain mid-stream
+    for c in range(len(modes)):
+        g2.set_state(c, g.get_state(c))
+    outs.append(g2.update(np.ascontiguousarray(x[:, b0 * 128:])))
+    yg = np.concatenate(outs, axis=1)
+    others = [c for c in range(len(modes)) if c not in pll]
+    assert_same(yg[others], yo[others], "non-SYNCAM channels next to SYNCAM ones")
+    a, b = yg[pll].astype(np.float64), yo[pll].astype(np.float64)
+    assert np.abs(b).max() > 300
+    assert np.abs(a - b).max() <= 2                                                  # a 1-LSB difference through two biquads
+    assert np.sqrt(np.mean((a - b) ** 2)) <= 1e-5 * np.sqrt(np.mean(b ** 2)) + 0.02   # 1e-5 relative RMS (+ the LSB flips of quiet channels)
+    assert (yg[pll] != yo[pll]).mean() < 0.01
