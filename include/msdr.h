@@ -236,6 +236,12 @@ int msdr_anr_update_device(msdr_anr *anr, int mode, int16_t *d_data, uint32_t n_
 int msdr_anr_get_state(msdr_anr *anr, uint32_t ch, msdr_anr_state *out);
 int msdr_anr_set_state(msdr_anr *anr, uint32_t ch, const msdr_anr_state *in);
 uint64_t msdr_anr_launch_count(const msdr_anr *anr);
+/* The same inside a receive chain, where the sketch has it: between the demodulation switch and the biquads (ANR_on, .ino:99,702).
+ * anr_on: 0 off, 1 notch, 2 noise reduction, per channel range.  Channels with ANR on (like channels in mode SYNCAM) are finished
+ * beside the fused kernel on scratch copies; all other channels are untouched.  LMS state survives switching off and on. */
+int msdr_chain_set_anr(msdr_chain *chain, uint32_t ch0, uint32_t nch, int anr_on);
+int msdr_chain_get_anr_state(msdr_chain *chain, uint32_t ch, msdr_anr_state *out);
+int msdr_chain_set_anr_state(msdr_chain *chain, uint32_t ch, const msdr_anr_state *in);
 
 /* ---- synchronous-AM demodulator with PLL: `case SYNCAM`, Minimal-SDR.ino:631-688 -------------------------------
  * Stand-alone stateful operator: the FIR-filtered I and Q streams [n_channels][stride] in, corr[0] narrowed to int16 out.

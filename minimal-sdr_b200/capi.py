@@ -106,6 +106,9 @@ SYMBOLS = {
     "msdr_anr_get_state": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(AnrState)]),
     "msdr_anr_set_state": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(AnrState)]),
     "msdr_anr_launch_count": (C.c_uint64, [C.c_void_p]),
+    "msdr_chain_set_anr": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int]),
+    "msdr_chain_get_anr_state": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(AnrState)]),
+    "msdr_chain_set_anr_state": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(AnrState)]),
     "msdr_syncam_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_uint32]),
     "msdr_syncam_destroy": (None, [C.c_void_p]),
     "msdr_syncam_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -121,6 +121,19 @@ class ReceiveChain:
     def setNotch(self, obj, stage, frequency, q=1.0, ch0=0, nch=None, fs=None):
         return self.biquad_set_coefficients(obj, stage, design.biquad_notch(frequency, q, fs or self.K["AUDIO_SAMPLE_RATE_EXACT"]), ch0, nch)
 
+    def set_anr(self, anr_on, ch0=0, nch=None):
+        """ANR_on of the sketch (Minimal-SDR.ino:99): 0 off, 1 LMS notch, 2 LMS noise reduction, between demodulation and the biquads."""
+        ch0, nch = self._rng(ch0, nch)
+        return self._ck(self._L.msdr_chain_set_anr(self.h, ch0, nch, int(anr_on)))
+
+    def get_anr_state(self, ch):
+        st = capi.AnrState()
+        self._ck(self._L.msdr_chain_get_anr_state(self.h, int(ch), C.byref(st)))
+        return st
+
+    def set_anr_state(self, ch, st):
+        return self._ck(self._L.msdr_chain_set_anr_state(self.h, int(ch), C.byref(st)))
+
     def set_option(self, key, value):
         return self._ck(self._L.msdr_chain_set_option(self.h, key.encode(), int(value)))
 

@@ -28,6 +28,8 @@ struct Params {
   size_t stride;
   uint32_t C, Cpad, n_blocks;
   int mode;      // 1 notch (output = error), 2 noise reduction (output = y), .ino:749-750
+  const uint8_t *row_mode; // optional per-row mode (0 = leave the row alone); overrides `mode`
+  const uint32_t *chmap;   // optional row -> state index (receive chain: its channels with ANR switched on)
   float *d;      // [kDline][Cpad]
   float *w;      // [kTaps][Cpad]
   float *lidx, *ngamma;
@@ -40,8 +42,10 @@ __global__ void __launch_bounds__(32) anr_kernel(const Params p)
   float *dl = reinterpret_cast<float *>(smem);                               // [kDline][32]
   uint32_t *buf = reinterpret_cast<uint32_t *>(smem + kDline * 32 * 4);      // [2][32][kPitchW]
   const int lane = threadIdx.x;
-  const uint32_t g = blockIdx.x, ch = g * kGroup + lane;
-  const bool active = ch < p.C;
+  const uint32_t g = blockIdx.x, row_id = g * kGroup + lane;
+  const int mode = row_id < p.C ? (p.row_mode ? (int)p.row_mode[row_id] : p.mode) : 0;
+  const bool active = row_id < p.C && mode != 0;
+  const uint32_t ch = active ? (p.chmap ? p.chmap[row_id] : row_id) : 0;
   const int nrows = min(kGroup, (int)(p.C - g * kGroup));
 
   const float two_mu = (float)0.001, gamma = (float)0.1, lidx_min = 0.0f, lidx_max = 200.0f, den_mult = (float)6.25e-10, lincr = 1.0f, ldecr = 3.0f;
@@ -90,7 +94,7 @@ __global__ void __launch_bounds__(32) anr_kernel(const Params p)
         }
         const float inv_sigp = __double2float_rn(__ddiv_rn(1.0, __dadd_rn((double)sigma, 1e-10)));
         const float error = __fsub_rn(dcur, y);
-        row[i] = (int16_t)__float2int_rz(p.mode == 1 ? error : y);
+        row[i] = (int16_t)__float2int_rz(mode == 1 ? error : y);
         float nel = __double2float_rn(__dmul_rn((double)error, __dsub_rn(1.0, (double)__fmul_rn(__fmul_rn(two_mu, sigma), inv_sigp))));
         if (nel < 0.0f) nel = -nel;
         const float t2 = __fmul_rn(__fmul_rn(__fmul_rn(two_mu, error), sigma), inv_sigp);
@@ -134,6 +138,24 @@ __global__ void __launch_bounds__(32) anr_kernel(const Params p)
 constexpr size_t kSmem = (size_t)kDline * 32 * 4 + 2 * kGroup * kPitchW * 4;
 
 } // namespace anr
+
+// rows of demodulated audio in place; per-row mode and state index (msdr_capi.cu: channels of a receive chain with ANR on)
+cudaError_t launch_anr(int16_t *data, size_t stride, uint32_t rows, uint32_t n_blocks, const uint8_t *row_mode, const uint32_t *chmap, float *d, float *w,
+                       float *lidx, float *ngamma, int *in_idx, uint32_t Cpad, cudaStream_t s)
+{
+  if (rows == 0 || n_blocks == 0) return cudaSuccess;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(anr::anr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)anr::kSmem);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  anr::Params p{};
+  p.data = data; p.stride = stride; p.C = rows; p.Cpad = Cpad; p.n_blocks = n_blocks; p.mode = 0; p.row_mode = row_mode; p.chmap = chmap;
+  p.d = d; p.w = w; p.lidx = lidx; p.ngamma = ngamma; p.in_idx = in_idx;
+  anr::anr_kernel<<<(rows + kGroup - 1) / kGroup, 32, anr::kSmem, s>>>(p);
+  return cudaGetLastError();
+}
 } // namespace msdr
 
 struct msdr_anr {
@@ -230,7 +252,7 @@ int msdr_anr_update_device(msdr_anr *anr, int mode, int16_t *d_data, uint32_t n_
   if (((uintptr_t)d_data & 15u) || (stride & 7u)) return anr_fail(anr, MSDR_ERR_ARGUMENT, "anr_update_device: buffer must be 16-byte aligned and stride a multiple of 8 samples");
   ACK(cudaSetDevice(anr->device));
   msdr::anr::Params p{};
-  p.data = d_data; p.stride = stride; p.C = anr->C; p.Cpad = anr->Cpad; p.n_blocks = n_blocks; p.mode = mode;
+  p.data = d_data; p.stride = stride; p.C = anr->C; p.Cpad = anr->Cpad; p.n_blocks = n_blocks; p.mode = mode; p.row_mode = nullptr; p.chmap = nullptr;
   p.d = anr->d_d; p.w = anr->d_w; p.lidx = anr->d_lidx; p.ngamma = anr->d_ngamma; p.in_idx = anr->d_in_idx;
   msdr::anr::anr_kernel<<<(anr->C + msdr::kGroup - 1) / msdr::kGroup, 32, msdr::anr::kSmem, anr->stream>>>(p);
   ACK(cudaGetLastError());

@@ -105,9 +105,16 @@ struct msdr_chain {
   // mode SYNCAM with the f32 PLL (.ino:631-688): a serial loop through sinf/cosf/atan2f per channel, run beside the fused kernel
   // on dense scratch copies of those channels (see syncam_lane_*)
   float *d_pll = nullptr;            // [3][Cpad] fil_out, omega2, phzerror
+  // LMS notch / noise reduction between demodulation and the biquads (.ino:702-770), per channel 0 = off, 1, 2; same lane
+  std::vector<uint8_t> h_anr;
+  uint32_t n_anr = 0;                // channels with ANR on
+  float *d_anr_d = nullptr, *d_anr_w = nullptr, *d_anr_lidx = nullptr, *d_anr_ngamma = nullptr; // allocated on first use
+  int *d_anr_idx = nullptr;
   struct PllLane {
     std::vector<uint32_t> rows;      // launch-relative rows, ordered by tap table
     uint32_t *d_rows = nullptr, *d_chmap = nullptr;
+    uint8_t *d_kind = nullptr, *d_anr_mode = nullptr;
+    bool any_pll = false, any_anr = false;
     int16_t *d_raw = nullptr, *d_I = nullptr, *d_Q = nullptr, *d_If = nullptr, *d_Qf = nullptr, *d_taps = nullptr;
     int32_t *d_defs = nullptr;
     size_t cap_rows = 0, cap_samples = 0;
@@ -280,6 +287,8 @@ void msdr_chain_destroy(msdr_chain *chain)
   cudaFree(chain->d_mode); cudaFree(chain->d_set); cudaFree(chain->d_hist); cudaFree(chain->d_bq);
   cudaFree(chain->plan.d_rowmap); cudaFree(chain->plan.d_grp); cudaFree(chain->plan.d_wave_rb0); cudaFree(chain->plan.d_rb); cudaFree(chain->plan.d_bmat);
   cudaFree(chain->d_tile_cnt); cudaFree(chain->d_pll);
+  cudaFree(chain->d_anr_d); cudaFree(chain->d_anr_w); cudaFree(chain->d_anr_lidx); cudaFree(chain->d_anr_ngamma); cudaFree(chain->d_anr_idx);
+  cudaFree(chain->pll.d_kind); cudaFree(chain->pll.d_anr_mode);
   cudaFree(chain->pll.d_rows); cudaFree(chain->pll.d_chmap); cudaFree(chain->pll.d_raw); cudaFree(chain->pll.d_I); cudaFree(chain->pll.d_Q);
   cudaFree(chain->pll.d_If); cudaFree(chain->pll.d_Qf); cudaFree(chain->pll.d_taps); cudaFree(chain->pll.d_defs);
   cudaFree(chain->d_sets); cudaFree(chain->d_set_kp4); cudaFree(chain->d_ctrl); cudaFree(chain->d_tile_flags);
@@ -324,6 +333,60 @@ int msdr_chain_set_mode(msdr_chain *chain, uint32_t ch0, uint32_t nch, int mode)
   CK(cudaSetDevice(chain->device));
   std::fill(chain->h_mode.begin() + ch0, chain->h_mode.begin() + ch0 + nch, (uint8_t)mode);
   CK(cudaMemsetAsync(chain->d_mode + ch0, mode, nch, chain->stream));
+  return MSDR_OK;
+}
+
+int msdr_chain_set_anr(msdr_chain *chain, uint32_t ch0, uint32_t nch, int anr_on)
+{
+  if (!chain) return MSDR_ERR_ARGUMENT;
+  if (!range_ok(chain, ch0, nch) || anr_on < 0 || anr_on > 2) return fail(chain, MSDR_ERR_ARGUMENT, "set_anr: bad channel range or ANR_on (0 off, 1 notch, 2 noise reduction)");
+  if (nch == 0) return MSDR_OK;
+  CK(cudaSetDevice(chain->device));
+  if (chain->h_anr.empty()) chain->h_anr.assign(chain->C, 0);
+  if (anr_on && !chain->d_anr_d) { // LMS state: 512-entry delay line + 64 weights per channel, allocated on first use
+    const size_t cp = chain->Cpad;
+    CK(cudaStreamSynchronize(chain->stream));
+    CK(cudaMalloc(&chain->d_anr_d, 512 * cp * 4)); CK(cudaMalloc(&chain->d_anr_w, 64 * cp * 4));
+    CK(cudaMalloc(&chain->d_anr_lidx, cp * 4)); CK(cudaMalloc(&chain->d_anr_ngamma, cp * 4)); CK(cudaMalloc(&chain->d_anr_idx, cp * 4));
+    CK(cudaMemset(chain->d_anr_d, 0, 512 * cp * 4)); CK(cudaMemset(chain->d_anr_w, 0, 64 * cp * 4)); CK(cudaMemset(chain->d_anr_idx, 0, cp * 4));
+    std::vector<float> l(cp, 120.0f), g(cp, 0.001f); // Minimal-SDR.ino:715,718
+    CK(cudaMemcpy(chain->d_anr_lidx, l.data(), cp * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(chain->d_anr_ngamma, g.data(), cp * 4, cudaMemcpyHostToDevice));
+  }
+  for (uint32_t c = ch0; c < ch0 + nch; ++c) {
+    chain->n_anr += (anr_on != 0) - (chain->h_anr[c] != 0);
+    chain->h_anr[c] = (uint8_t)anr_on; // the LMS state is kept across on/off like the sketch's statics
+  }
+  return MSDR_OK;
+}
+
+int msdr_chain_get_anr_state(msdr_chain *chain, uint32_t ch, msdr_anr_state *out)
+{
+  if (!chain || !out || ch >= chain->C) return MSDR_ERR_ARGUMENT;
+  if (!chain->d_anr_d) return fail(chain, MSDR_ERR_NOT_INITIALISED, "get_anr_state: ANR was never switched on in this chain");
+  CK(cudaSetDevice(chain->device));
+  CK(cudaStreamSynchronize(chain->stream));
+  const size_t pitch = (size_t)chain->Cpad * 4;
+  CK(cudaMemcpy2D(out->d, 4, chain->d_anr_d + ch, pitch, 4, 512, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy2D(out->w, 4, chain->d_anr_w + ch, pitch, 4, 64, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(&out->lidx, chain->d_anr_lidx + ch, 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(&out->ngamma, chain->d_anr_ngamma + ch, 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(&out->in_idx, chain->d_anr_idx + ch, 4, cudaMemcpyDeviceToHost));
+  return MSDR_OK;
+}
+
+int msdr_chain_set_anr_state(msdr_chain *chain, uint32_t ch, const msdr_anr_state *in)
+{
+  if (!chain || !in || ch >= chain->C || in->in_idx < 0 || in->in_idx >= 512) return MSDR_ERR_ARGUMENT;
+  if (!chain->d_anr_d) return fail(chain, MSDR_ERR_NOT_INITIALISED, "set_anr_state: switch ANR on (msdr_chain_set_anr) first");
+  CK(cudaSetDevice(chain->device));
+  CK(cudaStreamSynchronize(chain->stream));
+  const size_t pitch = (size_t)chain->Cpad * 4;
+  CK(cudaMemcpy2D(chain->d_anr_d + ch, pitch, in->d, 4, 4, 512, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy2D(chain->d_anr_w + ch, pitch, in->w, 4, 4, 64, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(chain->d_anr_lidx + ch, &in->lidx, 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(chain->d_anr_ngamma + ch, &in->ngamma, 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(chain->d_anr_idx + ch, &in->in_idx, 4, cudaMemcpyHostToDevice));
   return MSDR_OK;
 }
 
@@ -459,20 +522,27 @@ int build_tc_plan(msdr_chain *chain, uint32_t ch0, uint32_t nch, uint32_t W)
 
 namespace {
 
-// ---- channels in mode SYNCAM without MSDR_FLAG_AM_Q31: the f32 PLL demodulator (Minimal-SDR.ino:631-688) -------------------------
-// The fused kernel has no serial PLL stage.  It processes these channels like any other (their result is thrown away); their
+// ---- channels the fused kernel cannot finish: mode SYNCAM without MSDR_FLAG_AM_Q31 (the f32 PLL demodulator, Minimal-SDR.ino:631-688)
+// and channels with the LMS notch / noise reduction switched on (.ino:702-770, between demodulation and the biquads) ---------------
+// The fused kernel has no serial PLL stage and no LMS stage.  It processes these channels like any other (their result is thrown away); their
 // real result is computed on dense scratch copies with the stage kernels and written over it:
 //   before the fused kernel   gather  hist || in  rows and the biquad words of both objects
 //   after it                  fs/4 mix -> FIR pair (zero initial state over hist || in: exact from sample 0 on, H >= taps - 1)
-//                             -> PLL (state per chain channel) -> biquad object 1, 2 -> scatter audio and biquad words back
+//                             -> demodulation switch or PLL (state per chain channel) -> LMS where it is on
+//                             -> biquad object 1, 2 -> scatter audio and biquad words back
 // The raw-sample history is the fused kernel's to update; it is correct for every channel.
 int syncam_lane_prepare(msdr_chain *chain, uint32_t ch0, uint32_t nch, const int16_t *d_in, size_t stride, uint32_t L)
 {
   msdr_chain::PllLane &ln = chain->pll;
   ln.rows.clear();
-  if (chain->flags & MSDR_FLAG_AM_Q31) return MSDR_OK; // Teensy 3.2 arithmetic: SYNCAM is the q31 envelope (.ino:618-620)
-  for (uint32_t r = 0; r < nch; ++r)
-    if (chain->h_mode[ch0 + r] == MSDR_MODE_SYNCAM) ln.rows.push_back(r);
+  ln.any_pll = ln.any_anr = false;
+  const bool pll_build = !(chain->flags & MSDR_FLAG_AM_Q31); // Teensy 3.2 arithmetic: SYNCAM is the q31 envelope (.ino:618-620)
+  for (uint32_t r = 0; r < nch; ++r) {
+    const bool is_pll = pll_build && chain->h_mode[ch0 + r] == MSDR_MODE_SYNCAM;
+    const bool is_anr = chain->n_anr && chain->h_anr[ch0 + r] != 0;
+    if (is_pll || is_anr) ln.rows.push_back(r);
+    ln.any_pll |= is_pll; ln.any_anr |= is_anr;
+  }
   if (ln.rows.empty()) return MSDR_OK;
   std::stable_sort(ln.rows.begin(), ln.rows.end(), [&](uint32_t a, uint32_t b) { return chain->h_set[ch0 + a] < chain->h_set[ch0 + b]; });
   const uint32_t n = (uint32_t)ln.rows.size();
@@ -480,19 +550,30 @@ int syncam_lane_prepare(msdr_chain *chain, uint32_t ch0, uint32_t nch, const int
   if (n > ln.cap_rows || samples > ln.cap_samples) {
     CK(cudaStreamSynchronize(chain->stream));
     cudaFree(ln.d_rows); cudaFree(ln.d_chmap); cudaFree(ln.d_raw); cudaFree(ln.d_I); cudaFree(ln.d_Q); cudaFree(ln.d_If); cudaFree(ln.d_Qf); cudaFree(ln.d_taps);
-    cudaFree(ln.d_defs);
+    cudaFree(ln.d_defs); cudaFree(ln.d_kind); cudaFree(ln.d_anr_mode);
+    ln.d_kind = ln.d_anr_mode = nullptr;
     ln.d_rows = ln.d_chmap = nullptr; ln.d_raw = ln.d_I = ln.d_Q = ln.d_If = ln.d_Qf = ln.d_taps = nullptr; ln.d_defs = nullptr;
     ln.cap_rows = ln.cap_samples = 0;
-    CK(cudaMalloc(&ln.d_rows, n * 4)); CK(cudaMalloc(&ln.d_chmap, n * 4)); CK(cudaMalloc(&ln.d_defs, (size_t)n * 64 * 4));
+    CK(cudaMalloc(&ln.d_rows, n * 4)); CK(cudaMalloc(&ln.d_chmap, n * 4)); CK(cudaMalloc(&ln.d_kind, n)); CK(cudaMalloc(&ln.d_anr_mode, n)); CK(cudaMalloc(&ln.d_defs, (size_t)n * 64 * 4));
     CK(cudaMalloc(&ln.d_taps, 2 * MSDR_MAX_TAPS * sizeof(int16_t)));
     CK(cudaMalloc(&ln.d_raw, samples * 2)); CK(cudaMalloc(&ln.d_I, samples * 2)); CK(cudaMalloc(&ln.d_Q, samples * 2));
     CK(cudaMalloc(&ln.d_If, samples * 2)); CK(cudaMalloc(&ln.d_Qf, samples * 2));
     ln.cap_rows = n; ln.cap_samples = samples;
   }
   std::vector<uint32_t> chmap(n);
-  for (uint32_t i = 0; i < n; ++i) chmap[i] = ch0 + ln.rows[i];
+  std::vector<uint8_t> kind(n), amode(n);
+  for (uint32_t i = 0; i < n; ++i) {
+    const uint32_t ch = ch0 + ln.rows[i];
+    chmap[i] = ch;
+    const int md = chain->h_mode[ch];
+    // demodulation kind of the row (Minimal-SDR.ino:589-628); 255 = the PLL demodulator takes the row
+    kind[i] = (pll_build && md == MSDR_MODE_SYNCAM) ? 255 : md == MSDR_MODE_LSB ? 0 : md == MSDR_MODE_USB ? 1 : (md == MSDR_MODE_SYNCAM || !pll_build) ? 3 : 2;
+    amode[i] = chain->n_anr ? chain->h_anr[ch] : 0;
+  }
   CK(cudaMemcpyAsync(ln.d_rows, ln.rows.data(), n * 4, cudaMemcpyHostToDevice, chain->stream));
   CK(cudaMemcpyAsync(ln.d_chmap, chmap.data(), n * 4, cudaMemcpyHostToDevice, chain->stream));
+  CK(cudaMemcpyAsync(ln.d_kind, kind.data(), n, cudaMemcpyHostToDevice, chain->stream));
+  CK(cudaMemcpyAsync(ln.d_anr_mode, amode.data(), n, cudaMemcpyHostToDevice, chain->stream));
   CK(cudaStreamSynchronize(chain->stream)); // the index vectors are temporaries / reused host storage
   CK(launch_gather_rows(ln.d_rows, n, ch0, chain->d_hist, chain->H, d_in, stride, ln.d_raw, L, chain->stream));
   CK(launch_bq_words(0, ln.d_rows, n, ch0, chain->d_bq, chain->Cpad, ln.d_defs, chain->stream));
@@ -521,7 +602,11 @@ int syncam_lane_finish(msdr_chain *chain, uint32_t ch0, int16_t *d_out, size_t s
     i0 = i1;
   }
   int16_t *audio = ln.d_I; // reuse: [n][Lp], audio in the first L samples of every row
-  CK(launch_syncam(ln.d_If + H, ln.d_Qf + H, Lp, audio, Lp, n, L, chain->d_pll, chain->Cpad, ln.d_chmap, chain->stream));
+  CK(launch_demod_rows(ln.d_kind, ln.d_If + H, ln.d_Qf + H, Lp, audio, Lp, n, L, chain->stream));
+  if (ln.any_pll) CK(launch_syncam(ln.d_If + H, ln.d_Qf + H, Lp, audio, Lp, n, L, chain->d_pll, chain->Cpad, ln.d_chmap, ln.d_kind, chain->stream));
+  if (ln.any_anr)
+    CK(launch_anr(audio, Lp, n, L / MSDR_BLOCK_SAMPLES, ln.d_anr_mode, ln.d_chmap, chain->d_anr_d, chain->d_anr_w, chain->d_anr_lidx, chain->d_anr_ngamma,
+                  chain->d_anr_idx, chain->Cpad, chain->stream));
   CK(launch_biquad(ln.d_defs, audio, n, L, Lp, chain->stream));
   CK(launch_biquad(ln.d_defs + (size_t)n * 32, audio, n, L, Lp, chain->stream));
   CK(launch_scatter_rows(ln.d_rows, n, audio, Lp, d_out, stride, L, chain->stream));

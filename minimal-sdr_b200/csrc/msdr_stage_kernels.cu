@@ -311,17 +311,37 @@ __global__ void bq_words_kernel(int dir, const uint32_t *__restrict__ rows, uint
   int32_t *d = defs + ((size_t)(w / 32u) * n + s) * 32u + (w % 32u);
   if (dir == 0) *d = *g; else *g = *d;
 }
+// demodulation switch with a kind per row (255 = leave the row alone); I/Q rows of pitch `stride`, output rows of pitch `ostride`
+__global__ void demod_rows_kernel(const uint8_t *__restrict__ kinds, const int16_t *__restrict__ I, const int16_t *__restrict__ Q, size_t stride,
+                                  int16_t *__restrict__ out, size_t ostride, uint32_t n)
+{
+  const uint32_t r = blockIdx.y;
+  const int kind = kinds[r];
+  if (kind > 3) return;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[r * ostride + i] = (int16_t)demod_sample(kind, I[r * stride + i], Q[r * stride + i]);
+}
+cudaError_t launch_demod_rows(const uint8_t *kinds, const int16_t *I, const int16_t *Q, size_t stride, int16_t *out, size_t ostride, uint32_t rows, uint32_t n,
+                              cudaStream_t s)
+{
+  if (rows == 0 || n == 0) return cudaSuccess;
+  for (uint32_t r0 = 0; r0 < rows; r0 += 32768u) // gridDim.y limit
+    demod_rows_kernel<<<dim3(8, std::min(rows - r0, 32768u)), 256, 0, s>>>(kinds + r0, I + (size_t)r0 * stride, Q + (size_t)r0 * stride, stride, out + (size_t)r0 * ostride, ostride, n);
+  return cudaGetLastError();
+}
 cudaError_t launch_gather_rows(const uint32_t *rows, uint32_t n, uint32_t ch0, const int16_t *hist, uint32_t H, const int16_t *in, size_t stride, int16_t *raw,
                                uint32_t L, cudaStream_t s)
 {
   if (n == 0) return cudaSuccess;
-  gather_rows_kernel<<<dim3(8, n), 256, 0, s>>>(rows, ch0, hist, H, in, stride, raw, L);
+  for (uint32_t r0 = 0; r0 < n; r0 += 32768u) // gridDim.y limit
+    gather_rows_kernel<<<dim3(8, std::min(n - r0, 32768u)), 256, 0, s>>>(rows + r0, ch0, hist, H, in, stride, raw + (size_t)r0 * ((size_t)H + L), L);
   return cudaGetLastError();
 }
 cudaError_t launch_scatter_rows(const uint32_t *rows, uint32_t n, const int16_t *audio, size_t astride, int16_t *out, size_t stride, uint32_t L, cudaStream_t s)
 {
   if (n == 0) return cudaSuccess;
-  scatter_rows_kernel<<<dim3(8, n), 256, 0, s>>>(rows, audio, astride, out, stride, L);
+  for (uint32_t r0 = 0; r0 < n; r0 += 32768u)
+    scatter_rows_kernel<<<dim3(8, std::min(n - r0, 32768u)), 256, 0, s>>>(rows + r0, audio + (size_t)r0 * astride, astride, out, stride, L);
   return cudaGetLastError();
 }
 cudaError_t launch_bq_words(int dir, const uint32_t *rows, uint32_t n, uint32_t ch0, int32_t *bq, uint32_t Cpad, int32_t *defs, cudaStream_t s)

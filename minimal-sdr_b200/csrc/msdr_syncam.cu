@@ -44,13 +44,14 @@ struct Params {
   float *state;         // [3][Cpad]: fil_out, omega2, phzerror
   uint32_t Cpad;
   const uint32_t *chmap; // row -> state index (NULL: identity); used by the receive chain for its SYNCAM channels
+  const uint8_t *row_sel; // optional: only rows with row_sel[row] == 255 are processed
   Consts k;
 };
 
 __global__ void __launch_bounds__(128) syncam_kernel(const Params p)
 {
   const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= p.C) return;
+  if (row >= p.C || (p.row_sel && p.row_sel[row] != 255)) return;
   const uint32_t ch = p.chmap ? p.chmap[row] : row;
   float fil_out = p.state[ch], omega2 = p.state[p.Cpad + ch], phzerror = p.state[2 * (size_t)p.Cpad + ch];
   const uint4 *pi = reinterpret_cast<const uint4 *>(p.I + (size_t)row * p.stride);
@@ -94,12 +95,12 @@ __global__ void __launch_bounds__(128) syncam_kernel(const Params p)
 
 // rows of filtered I/Q -> audio, PLL state indexed through chmap (msdr_capi.cu: SYNCAM channels of a receive chain)
 cudaError_t launch_syncam(const int16_t *I, const int16_t *Q, size_t stride, int16_t *out, size_t ostride, uint32_t rows, uint32_t n, float *state,
-                          uint32_t Cpad, const uint32_t *chmap, cudaStream_t s)
+                          uint32_t Cpad, const uint32_t *chmap, const uint8_t *row_sel, cudaStream_t s)
 {
   if (rows == 0 || n == 0) return cudaSuccess;
   static const syncam::Consts k = syncam::make_consts();
   syncam::Params p{};
-  p.I = I; p.Q = Q; p.out = out; p.stride = stride; p.ostride = ostride; p.C = rows; p.n = n; p.state = state; p.Cpad = Cpad; p.chmap = chmap; p.k = k;
+  p.I = I; p.Q = Q; p.out = out; p.stride = stride; p.ostride = ostride; p.C = rows; p.n = n; p.state = state; p.Cpad = Cpad; p.chmap = chmap; p.row_sel = row_sel; p.k = k;
   syncam::syncam_kernel<<<(rows + 127) / 128, 128, 0, s>>>(p);
   return cudaGetLastError();
 }
@@ -179,7 +180,7 @@ int msdr_syncam_update_device(msdr_syncam *sc, const int16_t *d_I, const int16_t
     return sc_fail(sc, MSDR_ERR_ARGUMENT, "syncam_update_device: buffers must be 16-byte aligned and stride a multiple of 8 samples");
   SCK(cudaSetDevice(sc->device));
   msdr::syncam::Params p{};
-  p.I = d_I; p.Q = d_Q; p.out = d_out; p.stride = stride; p.ostride = stride; p.chmap = nullptr; p.C = sc->C; p.n = n_blocks * MSDR_BLOCK_SAMPLES; p.state = sc->d_state; p.Cpad = sc->Cpad; p.k = sc->k;
+  p.I = d_I; p.Q = d_Q; p.out = d_out; p.stride = stride; p.ostride = stride; p.chmap = nullptr; p.row_sel = nullptr; p.C = sc->C; p.n = n_blocks * MSDR_BLOCK_SAMPLES; p.state = sc->d_state; p.Cpad = sc->Cpad; p.k = sc->k;
   msdr::syncam::syncam_kernel<<<(sc->C + 127) / 128, 128, 0, sc->stream>>>(p);
   SCK(cudaGetLastError());
   sc->launches++;

@@ -257,7 +257,12 @@ typedef struct {
   orc_fir *fir_i, *fir_q;
   orc_biquad bq[2];
   float pll[3]; /* SYNCAM PLL: fil_out, omega2, phzerror (.ino:643-645) */
+  int anr_on;   /* ANR_on (.ino:99): 0 off, 1 notch, 2 noise reduction */
+  void *anr;    /* LMS state, allocated when first switched on */
 } orc_channel;
+/* the LMS block of demodulation() (.ino:702-770), between the demodulation switch and the DAC queue; defined below */
+void *orc_anr_alloc1(void);
+void orc_anr_block_v(void *state, int mode, int16_t *p_dac, uint32_t n);
 /* `case SYNCAM` on the Teensy 3.5/3.6 (f32 PLL, .ino:631-688); defined with the other next-row restatements below */
 void orc_syncam_block3(float *state3, const int16_t *I_buffer, const int16_t *Q_buffer, int16_t *p_dac, uint32_t n);
 
@@ -279,7 +284,7 @@ orc_chain *orc_chain_new(uint32_t n_channels, int am_q31)
 void orc_chain_free(orc_chain *c)
 {
   if (!c) return;
-  for (uint32_t i = 0; i < c->n_channels; i++) { orc_fir_free(c->ch[i].fir_i); orc_fir_free(c->ch[i].fir_q); }
+  for (uint32_t i = 0; i < c->n_channels; i++) { orc_fir_free(c->ch[i].fir_i); orc_fir_free(c->ch[i].fir_q); free(c->ch[i].anr); }
   free(c->ch); free(c);
 }
 int orc_chain_set_mode(orc_chain *c, uint32_t ch0, uint32_t nch, int mode)
@@ -319,6 +324,15 @@ int orc_chain_biquad_set_coefficients(orc_chain *c, int obj, uint32_t ch0, uint3
 }
 /* state access for checkpoint/resume tests: raw FIR history is reconstructed from the I/Q delay lines
  * (even positions live in the I line, odd ones in the Q line; samples at n%4 in {2,3} were negated). */
+int orc_chain_set_anr(orc_chain *c, uint32_t ch0, uint32_t nch, int anr_on)
+{
+  if ((uint64_t)ch0 + nch > c->n_channels || anr_on < 0 || anr_on > 2) return -1;
+  for (uint32_t i = ch0; i < ch0 + nch; i++) {
+    if (anr_on && !c->ch[i].anr) c->ch[i].anr = orc_anr_alloc1();
+    c->ch[i].anr_on = anr_on;
+  }
+  return 0;
+}
 void orc_chain_get_biquad_definition(orc_chain *c, uint32_t ch, int obj, int32_t *out32) { memcpy(out32, c->ch[ch].bq[obj].definition, 128); }
 
 static int orc_demod_kind(const orc_chain *c, int mode)
@@ -353,6 +367,7 @@ int orc_chain_run(orc_chain *c, const int16_t *in, int16_t *out, uint32_t n_bloc
       orc_fir_run(k->fir_q, Q, Qf, ORC_BLOCK);
       if (k->mode == ORC_SYNCAM && !c->am_q31) orc_syncam_block3(k->pll, If, Qf, p_dac, ORC_BLOCK);
       else orc_demod(kind, If, Qf, p_dac, ORC_BLOCK);
+      if (k->anr_on > 0 && k->anr) orc_anr_block_v(k->anr, k->anr_on, p_dac, ORC_BLOCK);
       orc_biquad_update(&k->bq[0], p_dac, ORC_BLOCK);
       orc_biquad_update(&k->bq[1], p_dac, ORC_BLOCK);
     }
@@ -591,6 +606,14 @@ void orc_anr_block(orc_anr *a, int mode, int16_t *p_dac, uint32_t n)
     a->in_idx = (a->in_idx + mask) & mask;
   }
 }
+
+void *orc_anr_alloc1(void)
+{
+  orc_anr *a = (orc_anr *)malloc(sizeof(orc_anr));
+  if (a) orc_anr_init(a);
+  return a;
+}
+void orc_anr_block_v(void *state, int mode, int16_t *p_dac, uint32_t n) { orc_anr_block((orc_anr *)state, mode, p_dac, n); }
 
 orc_anr *orc_anr_new(uint32_t n_channels)
 {

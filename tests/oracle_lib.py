@@ -214,6 +214,13 @@ class CheckerChain:
         return self.L._f["chain_fir_set_coefficients"](self.h, ch0, nch, np.ascontiguousarray(cI, np.int16),
                                                        np.ascontiguousarray(cQ, np.int16))
 
+    def set_anr(self, ch0, nch, anr_on):
+        """ANR_on (Minimal-SDR.ino:99); only the plain-C oracle has it in its chain (the compiled reference's block is pinned separately)."""
+        f = self.L.lib.orc_chain_set_anr
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int]
+        return f(self.h, ch0, nch, int(anr_on))
+
     def biquad_set_coefficients(self, obj, ch0, nch, stage, coef):
         return self.L._f["chain_biquad_set_coefficients"](self.h, obj, ch0, nch, stage,
                                                           np.ascontiguousarray(coef, np.int32))

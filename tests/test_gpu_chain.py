@@ -347,3 +347,54 @@ def test_syncam_channels_in_a_chain(msdr, orc, K):
     assert np.abs(a - b).max() <= 2                                                  # a 1-LSB difference through two biquads
     assert np.sqrt(np.mean((a - b) ** 2)) <= 1e-5 * np.sqrt(np.mean(b ** 2)) + 0.02   # 1e-5 relative RMS (+ the LSB flips of quiet channels)
     assert (yg[pll] != yo[pll]).mean() < 0.01
+
+
+def test_anr_channels_in_a_chain(msdr, orc, K):
+    """ANR_on per channel (LMS notch = 1 / noise reduction = 2, Minimal-SDR.ino:702-770) sits between demodulation and the biquads.
+    The float LMS is bit-exact, so channels with ANR on are bit-exact too; ANR is switched on and off mid-stream (its state is
+    kept), channels migrate with their LMS state; a SYNCAM + ANR channel meets the float tolerance."""
+    modes = msdr.synth.mixed_modes(40)
+    modes[9] = SYNCAM
+    x = msdr.synth.batch(modes, 128 * 48)
+    g, _ = configure_pair(msdr, orc, K, modes)
+    notch_ch, nr_ch = [1, 2, 3, 9, 33], [16, 17, 39]
+
+    def set_anr(gg, chans, v):
+        for c in chans:
+            gg.set_anr(v, c, 1)
+    outs = [g.update(np.ascontiguousarray(x[:, :128 * 4]))]           # ANR off everywhere
+    set_anr(g, notch_ch, 1)
+    set_anr(g, nr_ch, 2)
+    outs.append(g.update(np.ascontiguousarray(x[:, 128 * 4:128 * 20])))
+    set_anr(g, [2], 0)                                              # off again for one channel ...
+    outs.append(g.update(np.ascontiguousarray(x[:, 128 * 20:128 * 30])))
+    set_anr(g, [2], 2)                                              # ... and back on in the other mode: the LMS state was kept
+    g2, _ = configure_pair(msdr, orc, K, modes)                        # migrate to a fresh chain
+    set_anr(g2, notch_ch, 1)
+    set_anr(g2, nr_ch, 2)
+    set_anr(g2, [2], 2)
+    for c in range(len(modes)):
+        g2.set_state(c, g.get_state(c))
+    for c in notch_ch + nr_ch:
+        g2.set_anr_state(c, g.get_anr_state(c))
+    outs.append(g2.update(np.ascontiguousarray(x[:, 128 * 30:])))
+    yg = np.concatenate(outs, axis=1)
+    # the oracle sees the same schedule
+    o2_parts = []
+    g_, oo = configure_pair(msdr, orc, K, modes)  # a second oracle chain driven through the same schedule at the same block boundaries
+    g_.close()
+    o2_parts.append(oo.run(np.ascontiguousarray(x[:, :128 * 4]))[0])
+    for c in notch_ch:
+        assert oo.set_anr(c, 1, 1) == 0
+    for c in nr_ch:
+        assert oo.set_anr(c, 1, 2) == 0
+    o2_parts.append(oo.run(np.ascontiguousarray(x[:, 128 * 4:128 * 20]))[0])
+    assert oo.set_anr(2, 1, 0) == 0
+    o2_parts.append(oo.run(np.ascontiguousarray(x[:, 128 * 20:128 * 30]))[0])
+    assert oo.set_anr(2, 1, 2) == 0
+    o2_parts.append(oo.run(np.ascontiguousarray(x[:, 128 * 30:]))[0])
+    yo = np.concatenate(o2_parts, axis=1)
+    exact = [c for c in range(len(modes)) if c != 9]
+    assert_same(yg[exact], yo[exact], "chain with ANR channels")
+    a, b = yg[9].astype(np.float64), yo[9].astype(np.float64)        # SYNCAM + notch: float tolerance
+    assert np.abs(a - b).max() <= 3 and np.sqrt(np.mean((a - b) ** 2)) <= 1e-4 * np.sqrt(np.mean(b ** 2)) + 0.05
