@@ -484,6 +484,8 @@ public:
   }
   // global `mode` + init_FIR() (Minimal-SDR.ino:901-930) for a channel range; tables are the caller's (the sketch's constants)
   int set_mode(int mode, uint32_t ch0 = 0, uint32_t nch = ~0u) { return status_ = msdr_chain_set_mode(chain_, ch0, cnt(ch0, nch), mode); }
+  // ANR_on of the sketch (.ino:99): 0 off, 1 LMS notch, 2 LMS noise reduction, between demodulation and the biquads
+  int set_ANR(int ANR_on, uint32_t ch0 = 0, uint32_t nch = ~0u) { return status_ = msdr_chain_set_anr(chain_, ch0, cnt(ch0, nch), ANR_on); }
   int init_FIR(uint16_t numTaps, const int16_t *cI, const int16_t *cQ, uint32_t ch0 = 0, uint32_t nch = ~0u)
   {
     return status_ = msdr_fir_init_q15(chain_, ch0, cnt(ch0, nch), numTaps, cI, cQ);
