@@ -212,6 +212,8 @@ int32_t msdr_amp_gain_multiplier(float gain);
 /* AudioAmplifier::update / applyGain (mixer.cpp:34-47,134-159) in place on host rows: SSAT16((multipliers[row] * x) >> 16).
  * Multiplier 65536 leaves the data unchanged and 0 gives zeros (the reference transmits no block at all for 0). */
 int msdr_op_amplifier(int device, const int32_t *multipliers, int16_t *data, uint32_t rows, uint32_t n, size_t stride);
+/* AudioOutputAnalog's sample formatting (output_dac.cpp:143): 12-bit DAC code = ((int16 sample) + 32768) >> 4. */
+int msdr_op_dac_codes(int device, const int16_t *in, uint16_t *out, uint32_t rows, uint32_t n, size_t stride);
 
 /* ---- LMS automatic notch / noise reduction: Minimal-SDR.ino:702-770 ------------------------------------------
  * The sketch runs it on p_dac between demodulation and queue_dac when ANR_on > 0 (1 = notch: output the LMS error, 2 = noise

@@ -941,6 +941,18 @@ int msdr_op_demod(int device, int kind, const int16_t *I, const int16_t *Q, int1
   return MSDR_OK;
 }
 
+int msdr_op_dac_codes(int device, const int16_t *in, uint16_t *out, uint32_t rows, uint32_t n, size_t stride)
+{
+  if (!in || !out || n > stride) return MSDR_ERR_ARGUMENT;
+  int st = op_begin(device); if (st) return st;
+  DevBuf a, b;
+  OPCK(a.alloc((size_t)rows * n * 2)); OPCK(b.alloc((size_t)rows * n * 2));
+  OPCK(cudaMemcpy2D(a.p, (size_t)n * 2, in, stride * 2, (size_t)n * 2, rows, cudaMemcpyHostToDevice));
+  OPCK(launch_dac_codes(a.as<int16_t>(), b.as<uint16_t>(), rows, n, n, nullptr));
+  OPCK(cudaMemcpy2D(out, stride * 2, b.p, (size_t)n * 2, (size_t)n * 2, rows, cudaMemcpyDeviceToHost));
+  return MSDR_OK;
+}
+
 int msdr_op_amplifier(int device, const int32_t *multipliers, int16_t *data, uint32_t rows, uint32_t n, size_t stride)
 {
   if (!multipliers || !data || n > stride) return MSDR_ERR_ARGUMENT;

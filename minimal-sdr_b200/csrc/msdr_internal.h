@@ -85,6 +85,7 @@ cudaError_t launch_anr(int16_t *data, size_t stride, uint32_t rows, uint32_t n_b
                        float *lidx, float *ngamma, int *in_idx, uint32_t Cpad, cudaStream_t s);
 cudaError_t launch_syncam(const int16_t *I, const int16_t *Q, size_t stride, int16_t *out, size_t ostride, uint32_t rows, uint32_t n, float *state,
                           uint32_t Cpad, const uint32_t *chmap, const uint8_t *row_sel, cudaStream_t s);
+cudaError_t launch_dac_codes(const int16_t *in, uint16_t *out, uint32_t rows, uint32_t n, size_t stride, cudaStream_t s);
 cudaError_t launch_amplifier(const int32_t *mult, int16_t *data, uint32_t rows, uint32_t n, size_t stride, cudaStream_t s);
 cudaError_t launch_biquad(int32_t *definition, int16_t *data, uint32_t rows, uint32_t n, size_t stride, cudaStream_t s);
 cudaError_t launch_freq_conv(int dir, int16_t *I, int16_t *Q, const int16_t *oscI, const int16_t *oscQ, uint32_t rows, uint32_t n, size_t stride,

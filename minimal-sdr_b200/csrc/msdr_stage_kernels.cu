@@ -136,6 +136,23 @@ cudaError_t launch_demod(int kind, const int16_t *I, const int16_t *Q, int16_t *
   return cudaGetLastError();
 }
 
+// ---- AudioOutputAnalog ISR (output_dac.cpp:140-144): int16 audio -> 12-bit DAC codes, ((s) + 32768) >> 4 ---------------------------
+__global__ void dac_codes_kernel(const int16_t *__restrict__ in, uint16_t *__restrict__ out, uint32_t rows, uint32_t n, size_t stride)
+{
+  const size_t total = (size_t)rows * n;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / n, off = r * stride + (i - r * n);
+    out[off] = (uint16_t)(((int)in[off] + 32768) >> 4);
+  }
+}
+cudaError_t launch_dac_codes(const int16_t *in, uint16_t *out, uint32_t rows, uint32_t n, size_t stride, cudaStream_t s)
+{
+  const size_t total = (size_t)rows * n;
+  if (total == 0) return cudaSuccess;
+  dac_codes_kernel<<<(int)std::min<size_t>((total + 255) / 256, 148 * 16), 256, 0, s>>>(in, out, rows, n, stride);
+  return cudaGetLastError();
+}
+
 // ---- AudioAmplifier::update / applyGain (mixer.cpp:34-47,134-159): SSAT16((mult * x) >> 16), one multiplier per row --------
 // (multiplier 65536 passes data through and 0 yields zeros: exactly what the formula gives; the reference transmits no block
 // at all for 0, which a caller handles by not forwarding the block)

@@ -89,3 +89,18 @@ def test_frontend_feeds_the_chain(msdr, forc, orc, K):
     xg, xo = fg.update(codes), fo.run(codes)
     assert_same(xg, xo, "front end")
     assert_same(g.update(xg), o.run(xo)[0], "front end + chain")
+
+
+def test_dac_codes_and_amplifier_ops(msdr, forc):
+    """msdr_op_dac_codes = ((s) + 32768) >> 4 (output_dac.cpp:143) on every int16 value; msdr_op_amplifier per-row multipliers."""
+    L = msdr.capi.lib()
+    s = np.arange(-32768, 32768, dtype=np.int32).astype(np.int16).reshape(8, 8192)
+    out = np.zeros(s.shape, np.uint16)
+    assert L.msdr_op_dac_codes(0, msdr.capi.ptr(s), msdr.capi.ptr(out), 8, 8192, 8192) == 0
+    assert np.array_equal(out, ((s.astype(np.int32) + 32768) >> 4).astype(np.uint16))
+    assert out.min() == 0 and out.max() == 4095
+    mults = np.array([forc.amp_multiplier(g) for g in (0.25, 1.0, 0.0, 1.7, -0.33, 40.0, 1e9, 0.999999)], np.int32)
+    d = s.copy()
+    assert L.msdr_op_amplifier(0, msdr.capi.ptr(mults), msdr.capi.ptr(d), 8, 8192, 8192) == 0
+    for r in range(8):
+        assert np.array_equal(d[r], forc.amp_apply(s[r], int(mults[r]))[0]), r
