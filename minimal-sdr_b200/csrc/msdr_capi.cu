@@ -115,6 +115,8 @@ struct msdr_chain {
     uint32_t *d_rows = nullptr, *d_chmap = nullptr;
     uint8_t *d_kind = nullptr, *d_anr_mode = nullptr;
     bool any_pll = false, any_anr = false;
+    bool dirty = true;                 // modes / ANR switches changed: rebuild `channels`
+    std::vector<uint32_t> channels;    // every chain channel that needs the lane, ascending
     int16_t *d_raw = nullptr, *d_I = nullptr, *d_Q = nullptr, *d_If = nullptr, *d_Qf = nullptr, *d_taps = nullptr;
     int32_t *d_defs = nullptr;
     size_t cap_rows = 0, cap_samples = 0;
@@ -332,6 +334,7 @@ int msdr_chain_set_mode(msdr_chain *chain, uint32_t ch0, uint32_t nch, int mode)
   if (nch == 0) return MSDR_OK;
   CK(cudaSetDevice(chain->device));
   std::fill(chain->h_mode.begin() + ch0, chain->h_mode.begin() + ch0 + nch, (uint8_t)mode);
+  chain->pll.dirty = true;
   CK(cudaMemsetAsync(chain->d_mode + ch0, mode, nch, chain->stream));
   return MSDR_OK;
 }
@@ -357,6 +360,7 @@ int msdr_chain_set_anr(msdr_chain *chain, uint32_t ch0, uint32_t nch, int anr_on
     chain->n_anr += (anr_on != 0) - (chain->h_anr[c] != 0);
     chain->h_anr[c] = (uint8_t)anr_on; // the LMS state is kept across on/off like the sketch's statics
   }
+  chain->pll.dirty = true;
   return MSDR_OK;
 }
 
@@ -537,10 +541,18 @@ int syncam_lane_prepare(msdr_chain *chain, uint32_t ch0, uint32_t nch, const int
   ln.rows.clear();
   ln.any_pll = ln.any_anr = false;
   const bool pll_build = !(chain->flags & MSDR_FLAG_AM_Q31); // Teensy 3.2 arithmetic: SYNCAM is the q31 envelope (.ino:618-620)
-  for (uint32_t r = 0; r < nch; ++r) {
+  if (ln.dirty) { // one scan per configuration change, not per update
+    ln.channels.clear();
+    for (uint32_t c = 0; c < chain->C; ++c)
+      if ((pll_build && chain->h_mode[c] == MSDR_MODE_SYNCAM) || (chain->n_anr && chain->h_anr[c] != 0)) ln.channels.push_back(c);
+    ln.dirty = false;
+  }
+  if (ln.channels.empty()) return MSDR_OK;
+  for (auto it = std::lower_bound(ln.channels.begin(), ln.channels.end(), ch0); it != ln.channels.end() && *it < ch0 + nch; ++it) {
+    const uint32_t r = *it - ch0;
     const bool is_pll = pll_build && chain->h_mode[ch0 + r] == MSDR_MODE_SYNCAM;
     const bool is_anr = chain->n_anr && chain->h_anr[ch0 + r] != 0;
-    if (is_pll || is_anr) ln.rows.push_back(r);
+    ln.rows.push_back(r);
     ln.any_pll |= is_pll; ln.any_anr |= is_anr;
   }
   if (ln.rows.empty()) return MSDR_OK;
