@@ -158,6 +158,19 @@ __device__ __forceinline__ uint32_t bq_word(BqStageD (&st)[NS], uint32_t w)
   return __byte_perm((uint32_t)ye, (uint32_t)yo, 0x5410);
 }
 
+// hybrid stage (feed-forward on the FP64 pipe): inputs sign-extended with one PRMT each, outputs arrive as y << 16
+template <int NS>
+__device__ __forceinline__ uint32_t bq_word(BqStageH (&st)[NS], uint32_t w)
+{
+  static_assert(NS == 1, "the hybrid stage is used one stage per warp");
+  int xe, xo; // prmt selector bit 3 replicates the sign of the selected byte: one instruction per sign extension
+  asm("prmt.b32 %0, %1, 0, 0x9910;" : "=r"(xe) : "r"(w));
+  asm("prmt.b32 %0, %1, 0, 0xBB32;" : "=r"(xo) : "r"(w));
+  const int ye = bq_step(st[0], xe);
+  const int yo = bq_step(st[0], xo);
+  return __byte_perm((uint32_t)ye, (uint32_t)yo, 0x7632);
+}
+
 __device__ __forceinline__ void bq_load_stage(BqStage &s, uint32_t &flag, const int32_t *__restrict__ bq, uint32_t Cpad, int obj, int stage, uint32_t ch)
 {
   const int32_t *b = bq + (size_t)((obj * 4 + stage) * 8) * Cpad + ch;
@@ -199,6 +212,26 @@ __device__ __forceinline__ void bq_store_stage(const BqStageD &s, uint32_t flag,
   b[7 * (size_t)Cpad] = (int32_t)((uint32_t)s.res | flag);
 }
 
+__device__ __forceinline__ void bq_load_stage(BqStageH &s, uint32_t &flag, const int32_t *__restrict__ bq, uint32_t Cpad, int obj, int stage, uint32_t ch)
+{
+  const int32_t *b = bq + (size_t)((obj * 4 + stage) * 8) * Cpad + ch;
+  bq_set_coefs(s, __ldcg(b + 0 * (size_t)Cpad), __ldcg(b + 1 * (size_t)Cpad), __ldcg(b + 2 * (size_t)Cpad), __ldcg(b + 3 * (size_t)Cpad),
+               __ldcg(b + 4 * (size_t)Cpad));
+  const uint32_t w5 = (uint32_t)__ldcg(b + 5 * (size_t)Cpad);
+  s.x1 = bq_d_from_int((int)w5 >> 16); s.x2 = bq_d_from_int((int)(short)(w5 & 0xFFFFu));
+  bq_unpack_hist((uint32_t)__ldcg(b + 6 * (size_t)Cpad), s.y1, s.y2);
+  const uint32_t w7 = (uint32_t)__ldcg(b + 7 * (size_t)Cpad);
+  s.res = (int)(w7 & 0x3FFFu);
+  flag = w7 & 0x80000000u;
+}
+__device__ __forceinline__ void bq_store_stage(const BqStageH &s, uint32_t flag, int32_t *__restrict__ bq, uint32_t Cpad, int obj, int stage, uint32_t ch)
+{
+  int32_t *b = bq + (size_t)((obj * 4 + stage) * 8) * Cpad + ch;
+  b[5 * (size_t)Cpad] = (int32_t)(((uint32_t)bq_int_from_d(s.x1) << 16) | ((uint32_t)bq_int_from_d(s.x2) & 0xFFFFu));
+  b[6 * (size_t)Cpad] = (int32_t)bq_pack_hist(s.y1, s.y2);
+  b[7 * (size_t)Cpad] = (int32_t)((uint32_t)s.res | flag);
+}
+
 
 // ---- one stage split in two (chain kernel v4, FF shape) ---------------------------------------------------------------
 // filter_biquad.cpp:56-63 per sample:  sum = res + b0 x[n] + b1 x[n-1] + b2 x[n-2] + a1 y[n-1] + a2 y[n-2]  (SMLAW products,
@@ -209,8 +242,8 @@ __device__ __forceinline__ void bq_store_stage(const BqStageD &s, uint32_t flag,
 // sub-partition stays free for the tensor-core epilogue and the converters that live there.
 struct BqFF {
   double b0, b1, b2; // coefficient * 2^-16
+  double m0, m1, m2; // 1.5 * 2^52 - 17 * coefficient: the low word of fma_rd(b', D, m) is the SMLAW product itself (msdr_device.cuh)
   double x1, x2;     // D-form input history
-  int negk;          // -17 * (b0 + b1 + b2)  (mod 2^32)
 };
 struct BqRec {
   int a1, a2; // already negated as stored by setCoefficients (filter_biquad.cpp:93-94)
@@ -221,16 +254,17 @@ struct BqRec {
 __device__ __forceinline__ int ff_step(BqFF &f, int x)
 {
   const double xD = bq_d_from_int(x);
-  const int e = bq_term_d(f.b0, xD) + bq_term_d(f.b1, f.x1) + bq_term_d(f.b2, f.x2) + f.negk;
+  const int e = __double2loint(__fma_rd(f.b0, xD, f.m0)) + __double2loint(__fma_rd(f.b1, f.x1, f.m1)) +
+                __double2loint(__fma_rd(f.b2, f.x2, f.m2));
   f.x2 = f.x1; f.x1 = xD;
   return e;
 }
 // returns y << 16
 __device__ __forceinline__ int rec_step(BqRec &r, int e)
 {
-  int pre;
-  asm("mad.hi.s32 %0, %1, %2, %3;" : "=r"(pre) : "r"(r.a2), "r"(r.y2), "r"(e));
-  pre += r.res;
+  int t, pre;
+  asm("mad.hi.s32 %0, %1, %2, %3;" : "=r"(t) : "r"(r.a2), "r"(r.y2), "r"(e));
+  asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(pre) : "r"(r.res), "r"(kBqOne), "r"(t)); // keeps res off the IMAD.HI chain (kBqOne)
   const int sum = smlaw_s(pre, r.a1, r.y1);
   int ys;
   asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(ys) : "r"(sum >> 14), "r"(0)); // ssat #16, asr #14, << 16
@@ -244,7 +278,7 @@ __device__ __forceinline__ void bq_load_ff(BqFF &f, const int32_t *__restrict__ 
   const int b0 = __ldcg(b + 0 * (size_t)Cpad), b1 = __ldcg(b + 1 * (size_t)Cpad), b2 = __ldcg(b + 2 * (size_t)Cpad);
   const double k = 1.0 / 65536.0;
   f.b0 = (double)b0 * k; f.b1 = (double)b1 * k; f.b2 = (double)b2 * k;
-  f.negk = (int)(0u - 17u * ((uint32_t)b0 + (uint32_t)b1 + (uint32_t)b2));
+  f.m0 = kBqM - 17.0 * (double)b0; f.m1 = kBqM - 17.0 * (double)b1; f.m2 = kBqM - 17.0 * (double)b2;
   const uint32_t w5 = (uint32_t)__ldcg(b + 5 * (size_t)Cpad); // (x[n-1] << 16) | (x[n-2] & 0xffff), filter_biquad.cpp:66-69
   f.x1 = bq_d_from_int((int)w5 >> 16);
   f.x2 = bq_d_from_int((int)(short)(w5 & 0xFFFFu));

@@ -1,7 +1,10 @@
 // bqstep2.cu — shorter recurrence for the biquad sample-step (one warp, isolated), verified against msdr::bq_step.
 // The step's critical path is  y[n-1] -> a1 product (+ early + res) -> >>14 -> clamp -> <<16.
-//   mode 0  reference bq_step: SHF, VIMNMX, VIMNMX, IMAD.U32(<<16), IMAD.HI
-//   mode 1  P : clamp and <<16 in one cvt.pack.sat.s16.s32 (I2IP)                      SHF, I2IP, IMAD.HI
+//   mode 0  msdr::bq_step as shipped: residual added through an opaque IMAD, so the loop-carried cycles are
+//           IMAD.HI(a1) -> SHF -> I2IP  and  IMAD.HI(a1) -> LOP3 -> IMAD
+//   mode 1  P : the same arithmetic with the residual added by a plain add: ptxas seeds ONE IMAD.HI chain through all five
+//           products with it (cycle = LOP3 + 5 dependent IMAD.HI)
+//   mode 7  H : msdr::bq_step(BqStageH): feed-forward products as exact DFMA.RM, a1/a2 products IMAD.HI
 //   mode 2  Q : a1 product split into 16-bit halves, no IMAD.HI on the path            SHF, VIMNMX x2, IMAD, SHF, IADD
 //   mode 3  Q': same with cvt.sat.s16.s32 for the clamp                                SHF, I2I.SAT, IMAD, SHF, IADD
 //   mode 4  P': like P but the >>14 folded: clamp(sum, -2^29, 2^29-1) has no cheap single op; uses shf + pack (same as 1) with
@@ -106,6 +109,9 @@ __global__ void k(long long *cyc, int *sink, int seed, int amp, int lanes)
   q.x1 = q.x2 = q.y1s = q.y2s = q.y1 = 0; q.res = 0;
   StR r;
   r.a1h = s.a1 >> 16; r.a1l = s.a1 & 0xFFFF; r.a2h = s.a2 >> 16; r.a2l = s.a2 & 0xFFFF; r.y1 = r.y2 = r.res = 0;
+  BqStageH sh;
+  bq_set_coefs(sh, s.b0, s.b1, s.b2, s.a1, s.a2);
+  sh.x1 = sh.x2 = bq_d_from_int(0); sh.y1 = sh.y2 = 0; sh.res = 0;
   int fx1 = 0, fx2 = 0;
   uint32_t x = threadIdx.x * 977u + seed;
   int acc = 0;
@@ -122,6 +128,7 @@ __global__ void k(long long *cyc, int *sink, int seed, int amp, int lanes)
       fx2 = fx1; fx1 = xs;
       v = step_rec(r, e);
     }
+    if (MODE == 7) v = bq_step(sh, xin) >> 16;        // hybrid: feed-forward on DFMA, recurrence on IMAD.HI
     if (MODE == 5) v = step_rec(r, (int)x >> 3);      // timing: e supplied
     if (MODE == 6) v = step_rec_hi(s, (int)x >> 3);   // timing: e supplied, IMAD.HI recurrence
     acc = acc * 31 + v;
@@ -159,11 +166,12 @@ int main()
   long long *d_cyc; int *d_sink;
   cudaMalloc(&d_cyc, 1024 * sizeof(long long)); cudaMalloc(&d_sink, (size_t)sms * 1024 * sizeof(int));
   std::vector<int> ref[2];
-  run<0>("0 bq_step (SHF,VIMNMX,VIMNMX,SHL,IMAD.HI)", d_cyc, d_sink, sms, ref);
-  run<1>("1 P  (SHF,I2IP.SAT,IMAD.HI)", d_cyc, d_sink, sms, ref);
+  run<0>("0 bq_step (residual via opaque IMAD)", d_cyc, d_sink, sms, ref);
+  run<1>("1 P  (plain add: 5 IMAD.HI serialised)", d_cyc, d_sink, sms, ref);
   run<2>("2 Q  (SHF,VIMNMX,VIMNMX,IMAD,SHF,IADD)", d_cyc, d_sink, sms, ref);
   run<3>("3 Q' (SHF,I2I.SAT,IMAD,SHF,IADD)", d_cyc, d_sink, sms, ref);
   run<4>("4 split recurrence, feed-forward in loop (verify)", d_cyc, d_sink, sms, ref);
+  run<7>("7 hybrid: 3 DFMA feed-forward + 2 IMAD.HI recurrence", d_cyc, d_sink, sms, ref);
   { std::vector<int> dummy[2]; dummy[0] = dummy[1] = std::vector<int>();
     run<5>("5 split recurrence, e supplied (timing only)", d_cyc, d_sink, sms, dummy, 31);
     run<6>("6 IMAD.HI recurrence, e supplied (timing only)", d_cyc, d_sink, sms, dummy, 31); }
