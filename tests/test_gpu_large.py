@@ -88,3 +88,53 @@ def test_two_waves_long_update_all_shapes_agree(msdr, orc, K):
     o.biquad_set_coefficients(0, 0, len(pick), 0, K["biquad1_lowpass_coef"])
     o.biquad_set_coefficients(1, 0, len(pick), 0, K["biquad2_notch_coef"])
     assert_same(outs[0].cpu().numpy()[pick], o.run(np.ascontiguousarray(x.cpu().numpy()[pick]))[0], "two waves, sampled channels")
+
+
+def test_c5_channel_count(msdr, orc, K):
+    """BASELINE config 5's channel count on one GPU: 2^20 channels (32768 groups, 111 waves of two chain sets per SM), two
+    updates of 4 blocks with state carried; sampled channels incl. mode-range, group and wave edges match the oracle, and a
+    shard cut out of the middle (what another GPU would own) gives the same bytes."""
+    import torch
+    C, nb = 1 << 20, 8
+    dev = torch.device("cuda:0")
+    x = msdr.synth.torch_batch(C, nb * 128, dev)
+    q = C // 4
+    ranges = [(ol.MODE_AM, 0), (ol.MODE_USB, q), (ol.MODE_LSB, 2 * q), (ol.MODE_CW, 3 * q)]
+
+    def make(c0, n):
+        g = msdr.ReceiveChain(n)
+        g.setup_like_sketch(ol.MODE_AM)
+        for md, start in ranges:
+            lo, hi = max(start, c0), min(start + q, c0 + n)
+            if md != ol.MODE_AM and lo < hi:
+                g.tune(md, lo - c0, hi - lo)
+        g.set_stream(torch.cuda.current_stream().cuda_stream)
+        return g
+
+    g = make(0, C)
+    y = torch.empty_like(x)
+    for h in range(2):
+        xs, ys = x[:, h * 512:(h + 1) * 512], y[:, h * 512:(h + 1) * 512]
+        g.update_device(xs.data_ptr(), ys.data_ptr(), nb // 2, x.stride(0))
+    torch.cuda.synchronize()
+    rng = np.random.default_rng(5)
+    pick = sorted(set([0, 31, 32, 9471, 9472, q - 1, q, q + 1, 2 * q - 1, 2 * q, 3 * q - 1, 3 * q, C - 33, C - 32, C - 1] + list(rng.integers(0, C, 25))))
+    idx = torch.tensor(pick, device=dev)
+    xh, yh = x[idx].cpu().numpy(), y[idx].cpu().numpy()
+    o = orc.chain(len(pick))
+    for i, c in enumerate(pick):
+        md = ranges[min(c // q, 3)][0]
+        o.set_mode(i, 1, md)
+        o.fir_init(i, 1, *tables_for(K, md))
+    o.biquad_set_coefficients(0, 0, len(pick), 0, K["biquad1_lowpass_coef"])
+    o.biquad_set_coefficients(1, 0, len(pick), 0, K["biquad2_notch_coef"])
+    assert_same(yh, o.run(np.ascontiguousarray(xh))[0], "C5 channel count, sampled channels")
+    assert int(y[idx].abs().max()) > 1000
+    # a shard across the USB/LSB boundary, fed everything in one update
+    c0, n = 2 * q - 3000, 6000
+    g3 = make(c0, n)
+    xs = x[c0:c0 + n].contiguous()
+    y3 = torch.empty_like(xs)
+    g3.update_device(xs.data_ptr(), y3.data_ptr(), nb, xs.stride(0))
+    torch.cuda.synchronize()
+    assert torch.equal(y3, y[c0:c0 + n])
