@@ -311,6 +311,9 @@ def test_every_kernel_shape_is_bit_exact(msdr, orc, K, variant, name):
     lp, notch = K["biquad1_lowpass_coef"], K["biquad2_notch_coef"]
     bq = [(0, 0, lp, 0, None), (1, 0, notch, 0, None)]
     bq += [(0, st, lp, 40, 10) for st in range(1, 4)] + [(1, st, lp, 100, 32) for st in range(1, 4)]
+    # b2 != b0 (band-pass / shelf shapes): a whole channel group of object 1, and single lanes of otherwise symmetric groups
+    asym = [int(0.31 * 2 ** 30), int(0.05 * 2 ** 30), int(-0.29 * 2 ** 30), int(1.1 * 2 ** 30), int(-0.6 * 2 ** 30)]
+    bq += [(0, 0, asym, 64, 32), (1, 0, asym, 130, 1), (0, 0, asym, 199, 1)]
     g, o = configure_pair(msdr, orc, K, modes, biquads=bq)
     g.set_option("variant", variant)
     cI, cQ = wrap_coeffs(86, rng), wrap_coeffs(86, rng)  # the accumulator wraps, outputs saturate
