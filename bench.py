@@ -366,6 +366,18 @@ def main():
         per_launch_s = (ms * 1e-3) / max(1, launches)
         samples_per_launch = samples_per_step * args.steps / max(1, launches)
         achieved = ALGO_BYTES_PER_SAMPLE * samples_per_launch / per_launch_s / 1e9
+        # second ceiling (SURVEY 8d asks for the issue-side fraction next to the HBM one): a channel group of 32 advances one
+        # sample per biquad sample-step of its chain warps, 43.5 cycles isolated (profiles/r01_microbench_lat.txt), and an SM
+        # hosts one group (two when there are more groups than SMs)
+        import torch
+        sms = torch.cuda.get_device_properties(0).multi_processor_count
+        groups = (C + 31) // 32
+        concurrent = groups if groups <= sms else min(groups, 2 * sms)
+        f_hz = float((clk or {}).get("sm_mhz") or 1965.0) * 1e6
+        rec_ceiling = min(C, concurrent * 32) * f_hz / 43.5 / 1e6
+        recurrence = {"bound": "serial biquad recurrence, issue-bound inside its warp", "cycles_per_sample_step": 43.5,
+                      "concurrent_channel_groups": int(concurrent), "ceiling": rec_ceiling, "unit": "Msamples/s per GPU",
+                      "frac": value / world / rec_ceiling, "source": "tools/microbench/bqstep2.cu, lat.cu; DESIGN.md section 6"}
         line = {
             "metric": "demodulated Msamples/s (all channels)", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -375,7 +387,7 @@ def main():
                          "traffic_source": ncu_traffic()[1], "algorithmic_bytes_per_launch": ALGO_BYTES_PER_SAMPLE * samples_per_launch,
                          "peak_source": peak_src, "kernel": "msdr::v4::chain_kernel (fused mix + tensor-core FIR pair + demod + biquad cascade)",
                          "algorithmic_bytes_per_sample": ALGO_BYTES_PER_SAMPLE, "samples_per_launch": samples_per_launch,
-                         "avg_launch_ms": per_launch_s * 1e3,
+                         "avg_launch_ms": per_launch_s * 1e3, "recurrence": recurrence,
                          "note": "not HBM-bound: 4096 channels are 128 biquad chains, each an exact-arithmetic serial recurrence of ~47 cycles per sample per warp; the FIR pair runs beside them on the tensor cores (tcgen05 kind::i8); see DESIGN.md section 6"},
             "e2e": e2e,
         }
