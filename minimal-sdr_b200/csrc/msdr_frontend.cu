@@ -7,8 +7,8 @@
 // Batch semantics: zero queue latency, block k+1 is amplified with the gain AGC set after block k.
 //
 // The high-pass is a truncating recurrence per sample and the AGC a feedback per block: serial in time per channel, parallel
-// over channels.  One warp owns 32 channels (lane = channel) for the whole call; blocks travel global -> shared (cp.async,
-// coalesced, double buffered) -> lane-per-row processing in place -> global.  Bound: per-sample dependent latency of the
+// over channels.  One warp owns 32 channels (lane = channel) for the whole call; half blocks travel global -> shared (cp.async,
+// coalesced, three buffers) -> lane-per-row processing in place -> global.  Bound: per-sample dependent latency of the
 // recurrence (~25 cycles) for few channels, HBM (4 B per sample) for many.
 #include "msdr_device.cuh"
 #include "msdr_internal.h"
@@ -21,7 +21,6 @@ namespace msdr {
 namespace fe {
 
 constexpr int kBlock = 128;                    // AUDIO_BLOCK_SAMPLES
-constexpr int kPitchW = kBlock / 2 + 4;        // shared row pitch in words (4 mod 32: conflict-free row-wise 128-bit access)
 constexpr int kAgcBuf = 25;                    // .ino:445
 constexpr int kCoefHpf = 1048300 << 10;        // input_adc.cpp:32, S1.30
 
@@ -96,9 +95,15 @@ struct Params {
   int agc_on;
 };
 
+// Shared memory decides how many of these one-warp CTAs an SM holds, and the kernel is latency-bound below ~24 warps per SM:
+// the blocks travel in halves (64 samples, 4.6 KB per buffer), three buffers deep, so a CTA costs 13.8 KB (16 per SM).
+constexpr int kPart = 64;                      // samples per staged piece (half an audio block)
+constexpr int kPartPitchW = kPart / 2 + 4;     // 36 words: 4 mod 32, conflict-free row-wise 128-bit access
+constexpr int kNBuf = 3;
+
 __global__ void __launch_bounds__(32) frontend_kernel(const Params p)
 {
-  __shared__ __align__(16) uint32_t buf[2][kGroup * kPitchW];
+  __shared__ __align__(16) uint32_t buf[kNBuf][kGroup * kPartPitchW];
   const int lane = threadIdx.x;
   const uint32_t g = blockIdx.x, row = g * kGroup + lane;
   const bool active = row < p.C;
@@ -106,76 +111,89 @@ __global__ void __launch_bounds__(32) frontend_kernel(const Params p)
   State s;
   if (active) s = p.state[row];
 
-  // coalesced mapping for the copies: 2 rows of 256 bytes per warp instruction
-  const int r0 = lane >> 4, c = lane & 15;
+  // coalesced mapping for the copies: 4 rows of 128 bytes per warp instruction
+  const int r0 = lane >> 3, c = lane & 7;
   const unsigned char *gin = reinterpret_cast<const unsigned char *>(p.adc + ((size_t)g * kGroup + r0) * p.stride) + c * 16;
   unsigned char *gout = reinterpret_cast<unsigned char *>(p.out + ((size_t)g * kGroup + r0) * p.stride) + c * 16;
-  const size_t gstep = 2 * p.stride * 2;
-  auto issue = [&](uint32_t b) {
-    const uint32_t sdst = smem_u32(buf[b & 1]) + (uint32_t)(r0 * kPitchW * 4 + c * 16);
+  const size_t gstep = 4 * p.stride * 2;
+  const uint32_t nparts = p.n_blocks * (kBlock / kPart);
+  auto issue = [&](uint32_t h) {
+    if (h < nparts) {
+      const uint32_t sdst = smem_u32(buf[h % kNBuf]) + (uint32_t)(r0 * kPartPitchW * 4 + c * 16);
 #pragma unroll
-    for (int j = 0; j < 16; ++j)
-      if (r0 + 2 * j < nrows)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst + (uint32_t)(j * 2 * kPitchW * 4)), "l"(gin + (size_t)b * kBlock * 2 + (size_t)j * gstep) : "memory");
-    asm volatile("cp.async.commit_group;" ::: "memory");
+      for (int j = 0; j < 8; ++j)
+        if (r0 + 4 * j < nrows)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst + (uint32_t)(j * 4 * kPartPitchW * 4)), "l"(gin + (size_t)h * kPart * 2 + (size_t)j * gstep) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory"); // one group per piece, empty past the end: the wait below stays uniform
   };
   issue(0);
-  for (uint32_t b = 0; b < p.n_blocks; ++b) {
-    if (b + 1 < p.n_blocks) { issue(b + 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
-    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+  issue(1);
+  int x1 = s.hpf_x1, y1 = s.hpf_y1;
+  uint32_t maxv = (uint32_t)(-32767), minv = 32767u; // .ino:457-458, as packed halfword pairs
+  for (uint32_t h = 0; h < nparts; ++h) {
+    issue(h + 2); // its buffer held piece h - 1, written back (and fenced by the __syncwarp) at the end of the last iteration
+    asm volatile("cp.async.wait_group 2;" ::: "memory");
     __syncwarp();
-    uint32_t *rowp = buf[b & 1] + lane * kPitchW;
+    uint32_t *rowp = buf[h % kNBuf] + lane * kPartPitchW;
     if (active) {
-      int x1 = s.hpf_x1, y1 = s.hpf_y1;
       const int mult = s.mult;
-      uint32_t maxv = (uint32_t)(-32767), minv = 32767u; // .ino:457-458, as packed halfword pairs
 #pragma unroll 1
-      for (int q = 0; q < kBlock / 8; ++q) {
+      for (int q = 0; q < kPart / 8; ++q) {
         uint4 v = *reinterpret_cast<const uint4 *>(rowp + 4 * q);
         uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           int o[2];
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int tmp = (int)(((w[i] >> (16 * h)) & 0xFFFFu) << 14);
+          for (int k = 0; k < 2; ++k) {
+            // the ALU pipe (shifts, min/max, logic) is this kernel's busiest unit: the code word is widened on the multiplier,
+            // both clamps are cvt.pack.sat (one I2IP each instead of a min/max pair), the gain product is one IMAD.HI
+            const uint32_t code = k ? __byte_perm(w[i], 0u, 0x4432) : __byte_perm(w[i], 0u, 0x4410);
+            const int tmp = (int)(code * 16384u);
             const int acc = (int)((uint32_t)y1 - (uint32_t)x1 + (uint32_t)tmp);
             y1 = (int)(((long long)acc * (long long)kCoefHpf) >> 30); // FRACMUL_SHL(acc, COEF, 1): bits [61:30] of the product
             x1 = tmp;
+            int ss; // SSAT16(y1 >> 14) in the upper half (signed_saturate_rshift, input_adc.cpp:209)
+            asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(ss) : "r"(y1 >> 14), "r"(0));
             // AudioAmplifier::update special-cases multiplier 0 (nothing transmitted -> zeros here) and 65536 (pass-through,
-            // mixer.cpp:139-151); SSAT16((mult * s) >> 16) gives exactly those values for them, so no branch per sample
-            o[h] = ssat16((int)(((long long)mult * (long long)ssat16(y1 >> 14)) >> 16));
+            // mixer.cpp:139-151); SSAT16((mult * s) >> 16) gives exactly those values for them, so no branch per sample.
+            // hi32(mult * (s << 16)) == (mult * s) >> 16
+            o[k] = __mulhi(mult, ss);
           }
-          w[i] = ((uint32_t)o[0] & 0xFFFFu) | ((uint32_t)o[1] << 16);
+          asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(w[i]) : "r"(o[1]), "r"(o[0])); // both SSAT16 and the packing
           maxv = __vmaxs2(maxv, w[i]); // SSUB16 + SEL: per-halfword signed maximum / minimum
           minv = __vmins2(minv, w[i]);
         }
         *reinterpret_cast<uint4 *>(rowp + 4 * q) = make_uint4(w[0], w[1], w[2], w[3]);
       }
-      s.hpf_x1 = x1; s.hpf_y1 = y1;
-      if (p.agc_on) {
-        // .ino:468-478, literally: the cross-halfword compares, abs() of the whole words, the final select
-        int mx = (int)maxv, mn = (int)minv;
-        uint32_t ge;
-        (void)ssub16(mx, mx >> 16, ge); mx = (int)sel((uint32_t)mx, (uint32_t)(mx >> 16), ge); // max of the two halfwords -> low half
-        (void)ssub16(mn >> 16, mn, ge); mn = (int)sel((uint32_t)mn, (uint32_t)(mn >> 16), ge); // min -> low half
-        mn = (int)(mn < 0 ? 0u - (uint32_t)mn : (uint32_t)mn);                                   // abs() of the WHOLE words
-        mx = (int)(mx < 0 ? 0u - (uint32_t)mx : (uint32_t)mx);
-        (void)ssub16(mx, mn, ge);
-        const uint32_t absmax = sel((uint32_t)mx, (uint32_t)mn, ge) & 0xFFFFu;
-        agc_update(s, absmax, p.agc_max);
+      if ((h % (kBlock / kPart)) == kBlock / kPart - 1) { // an audio block is complete
+        if (p.agc_on) {
+          // .ino:468-478, literally: the cross-halfword compares, abs() of the whole words, the final select
+          int mx = (int)maxv, mn = (int)minv;
+          uint32_t ge;
+          (void)ssub16(mx, mx >> 16, ge); mx = (int)sel((uint32_t)mx, (uint32_t)(mx >> 16), ge); // max of the two halfwords -> low half
+          (void)ssub16(mn >> 16, mn, ge); mn = (int)sel((uint32_t)mn, (uint32_t)(mn >> 16), ge); // min -> low half
+          mn = (int)(mn < 0 ? 0u - (uint32_t)mn : (uint32_t)mn);                                   // abs() of the WHOLE words
+          mx = (int)(mx < 0 ? 0u - (uint32_t)mx : (uint32_t)mx);
+          (void)ssub16(mx, mn, ge);
+          const uint32_t absmax = sel((uint32_t)mx, (uint32_t)mn, ge) & 0xFFFFu;
+          agc_update(s, absmax, p.agc_max);
+        }
+        maxv = (uint32_t)(-32767); minv = 32767u;
       }
     }
     __syncwarp();
-    { // write the block back, coalesced
-      const unsigned char *ssrc = reinterpret_cast<const unsigned char *>(buf[b & 1]) + r0 * kPitchW * 4 + c * 16;
+    { // write the piece back, coalesced
+      const unsigned char *ssrc = reinterpret_cast<const unsigned char *>(buf[h % kNBuf]) + r0 * kPartPitchW * 4 + c * 16;
 #pragma unroll
-      for (int j = 0; j < 16; ++j)
-        if (r0 + 2 * j < nrows)
-          *reinterpret_cast<uint4 *>(gout + (size_t)b * kBlock * 2 + (size_t)j * gstep) = *reinterpret_cast<const uint4 *>(ssrc + j * 2 * kPitchW * 4);
+      for (int j = 0; j < 8; ++j)
+        if (r0 + 4 * j < nrows)
+          *reinterpret_cast<uint4 *>(gout + (size_t)h * kPart * 2 + (size_t)j * gstep) = *reinterpret_cast<const uint4 *>(ssrc + j * 4 * kPartPitchW * 4);
     }
-    __syncwarp(); // buf[b & 1] is the target of the copy issued in the next iteration but one
+    __syncwarp(); // this buffer is the target of the copy issued at the top of the next iteration
   }
+  s.hpf_x1 = x1; s.hpf_y1 = y1;
   if (active) p.state[row] = s;
 }
 
