@@ -95,14 +95,14 @@ struct Params {
   int agc_on;
 };
 
-// Shared memory decides how many of these one-warp CTAs an SM holds, and the kernel is latency-bound below ~24 warps per SM:
-// the blocks travel in halves (64 samples, 4.6 KB per buffer), three buffers deep, so a CTA costs 13.8 KB (16 per SM).
-constexpr int kPart = 64;                      // samples per staged piece (half an audio block)
-constexpr int kPartPitchW = kPart / 2 + 4;     // 36 words: 4 mod 32, conflict-free row-wise 128-bit access
-constexpr int kNBuf = 3;
-
+// Shared memory decides how many of these one-warp CTAs an SM holds: the blocks travel in pieces of kPart samples through a
+// ring of kNBuf buffers (64 samples, three deep: 13.8 KB per CTA, 16 CTAs per SM).
+template <int kPart, int kNBuf>
 __global__ void __launch_bounds__(32) frontend_kernel(const Params p)
 {
+  constexpr int kPartPitchW = kPart / 2 + 4;     // 4 mod 32, conflict-free row-wise 128-bit access
+  constexpr int RPI = 512 / (kPart * 2);         // rows per warp instruction
+  constexpr int CPR = 32 / RPI;                  // 16-byte chunks per row
   __shared__ __align__(16) uint32_t buf[kNBuf][kGroup * kPartPitchW];
   const int lane = threadIdx.x;
   const uint32_t g = blockIdx.x, row = g * kGroup + lane;
@@ -112,28 +112,28 @@ __global__ void __launch_bounds__(32) frontend_kernel(const Params p)
   if (active) s = p.state[row];
 
   // coalesced mapping for the copies: 4 rows of 128 bytes per warp instruction
-  const int r0 = lane >> 3, c = lane & 7;
+  const int r0 = lane / CPR, c = lane % CPR;
   const unsigned char *gin = reinterpret_cast<const unsigned char *>(p.adc + ((size_t)g * kGroup + r0) * p.stride) + c * 16;
   unsigned char *gout = reinterpret_cast<unsigned char *>(p.out + ((size_t)g * kGroup + r0) * p.stride) + c * 16;
-  const size_t gstep = 4 * p.stride * 2;
+  const size_t gstep = (size_t)RPI * p.stride * 2;
   const uint32_t nparts = p.n_blocks * (kBlock / kPart);
   auto issue = [&](uint32_t h) {
     if (h < nparts) {
       const uint32_t sdst = smem_u32(buf[h % kNBuf]) + (uint32_t)(r0 * kPartPitchW * 4 + c * 16);
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (r0 + 4 * j < nrows)
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst + (uint32_t)(j * 4 * kPartPitchW * 4)), "l"(gin + (size_t)h * kPart * 2 + (size_t)j * gstep) : "memory");
+      for (int j = 0; j < 32 / RPI; ++j)
+        if (r0 + RPI * j < nrows)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst + (uint32_t)(j * RPI * kPartPitchW * 4)), "l"(gin + (size_t)h * kPart * 2 + (size_t)j * gstep) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory"); // one group per piece, empty past the end: the wait below stays uniform
   };
-  issue(0);
-  issue(1);
+#pragma unroll
+  for (int i = 0; i < kNBuf - 1; ++i) issue(i);
   int x1 = s.hpf_x1, y1 = s.hpf_y1;
   uint32_t maxv = (uint32_t)(-32767), minv = 32767u; // .ino:457-458, as packed halfword pairs
   for (uint32_t h = 0; h < nparts; ++h) {
-    issue(h + 2); // its buffer held piece h - 1, written back (and fenced by the __syncwarp) at the end of the last iteration
-    asm volatile("cp.async.wait_group 2;" ::: "memory");
+    issue(h + kNBuf - 1); // its buffer held piece h - 1, written back (and fenced by the __syncwarp) at the end of the last iteration
+    asm volatile("cp.async.wait_group %0;" ::"n"(kNBuf - 1) : "memory");
     __syncwarp();
     uint32_t *rowp = buf[h % kNBuf] + lane * kPartPitchW;
     if (active) {
@@ -187,9 +187,9 @@ __global__ void __launch_bounds__(32) frontend_kernel(const Params p)
     { // write the piece back, coalesced
       const unsigned char *ssrc = reinterpret_cast<const unsigned char *>(buf[h % kNBuf]) + r0 * kPartPitchW * 4 + c * 16;
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (r0 + 4 * j < nrows)
-          *reinterpret_cast<uint4 *>(gout + (size_t)h * kPart * 2 + (size_t)j * gstep) = *reinterpret_cast<const uint4 *>(ssrc + j * 4 * kPartPitchW * 4);
+      for (int j = 0; j < 32 / RPI; ++j)
+        if (r0 + RPI * j < nrows)
+          *reinterpret_cast<uint4 *>(gout + (size_t)h * kPart * 2 + (size_t)j * gstep) = *reinterpret_cast<const uint4 *>(ssrc + j * RPI * kPartPitchW * 4);
     }
     __syncwarp(); // this buffer is the target of the copy issued at the top of the next iteration
   }
@@ -302,7 +302,9 @@ int msdr_frontend_update_device(msdr_frontend *fe, const uint16_t *d_adc, int16_
   msdr::fe::Params p{};
   p.adc = d_adc; p.out = d_out; p.stride = stride; p.C = fe->C; p.n_blocks = n_blocks; p.state = fe->d_state;
   p.agc_max = fe->agc_max; p.agc_on = fe->agc_on;
-  msdr::fe::frontend_kernel<<<(fe->C + msdr::kGroup - 1) / msdr::kGroup, 32, 0, fe->stream>>>(p);
+  // piece length / ring depth measured at 65 536 and 262 144 channels (profiles/r01_frontend.txt): <64, 3> 1018 / 1189 Gsamples/s,
+  // <128, 2> 914 / 1225, <64, 2> 1043 / 1153, <32, 4> 1040 / 1125, <32, 3> 1031 / 1027, <64, 4> 884 / 1195
+  msdr::fe::frontend_kernel<64, 3><<<(fe->C + msdr::kGroup - 1) / msdr::kGroup, 32, 0, fe->stream>>>(p);
   FCK(cudaGetLastError());
   fe->launches++;
   return MSDR_OK;
