@@ -97,6 +97,21 @@ __device__ __forceinline__ int step_rec_hi(BqStage &s, int e) // same with IMAD.
   return y;
 }
 
+// recurrence with the feed-forward sum supplied, residual kept off the IMAD.HI chain (what msdr::rec_step does)
+struct StB { int a1, a2, y1, y2, res; };
+__device__ __forceinline__ int step_rec_b(StB &r, int e)
+{
+  int t, pre;
+  asm("mad.hi.s32 %0, %1, %2, %3;" : "=r"(t) : "r"(r.a2), "r"(r.y2), "r"(e));
+  asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(pre) : "r"(r.res), "r"(kBqOne), "r"(t));
+  const int sum = smlaw_s(pre, r.a1, r.y1);
+  int ys;
+  asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(ys) : "r"(sum >> 14), "r"(0));
+  r.res = sum & 0x3FFF;
+  r.y2 = r.y1; r.y1 = ys;
+  return ys;
+}
+
 template <int MODE>
 __global__ void k(long long *cyc, int *sink, int seed, int amp, int lanes)
 {
@@ -115,7 +130,24 @@ __global__ void k(long long *cyc, int *sink, int seed, int amp, int lanes)
   int fx1 = 0, fx2 = 0;
   uint32_t x = threadIdx.x * 977u + seed;
   int acc = 0;
+  StB rb; rb.a1 = s.a1; rb.a2 = s.a2; rb.y1 = rb.y2 = rb.res = 0;
   long long t0 = clock64();
+  if (MODE == 10) { // batched hybrid: the feed-forward sums of 8 samples first (DFMA), then their 8 recurrence steps
+#pragma unroll 1
+    for (int n = 0; n < STEPS; n += 8) {
+      int e[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        x = x * 1664525u + 1013904223u;
+        const int xin = ((int)x >> 16) >> amp;
+        const double xD = bq_d_from_int(xin);
+        e[j] = __double2loint(__fma_rd(sh.b0, xD, sh.m0)) + __double2loint(__fma_rd(sh.b1, sh.x1, sh.m1)) + __double2loint(__fma_rd(sh.b2, sh.x2, sh.m2));
+        sh.x2 = sh.x1; sh.x1 = xD;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc = acc * 31 + (step_rec_b(rb, e[j]) >> 16);
+    }
+  } else
 #pragma unroll 8
   for (int n = 0; n < STEPS; ++n) {
     x = x * 1664525u + 1013904223u;
@@ -171,6 +203,7 @@ int main()
   run<2>("2 Q  (SHF,VIMNMX,VIMNMX,IMAD,SHF,IADD)", d_cyc, d_sink, sms, ref);
   run<3>("3 Q' (SHF,I2I.SAT,IMAD,SHF,IADD)", d_cyc, d_sink, sms, ref);
   run<4>("4 split recurrence, feed-forward in loop (verify)", d_cyc, d_sink, sms, ref);
+  run<10>("10 hybrid, batched: 8 feed-forward sums, then 8 recurrence steps", d_cyc, d_sink, sms, ref);
   run<7>("7 hybrid: 3 DFMA feed-forward + 2 IMAD.HI recurrence", d_cyc, d_sink, sms, ref);
   { std::vector<int> dummy[2]; dummy[0] = dummy[1] = std::vector<int>();
     run<5>("5 split recurrence, e supplied (timing only)", d_cyc, d_sink, sms, dummy, 31);

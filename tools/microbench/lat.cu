@@ -58,6 +58,32 @@ __global__ void k(long long *cyc, int *sink, int a, int one, int sh, int zero)
         asm volatile("mad.hi.s32 %0, %1, %0, %2;" : "+r"(d) : "r"(a), "r"(c));
         asm volatile("mad.hi.s32 %0, %1, %0, %2;" : "+r"(f) : "r"(a), "r"(e)); asm volatile("mad.hi.s32 %0, %1, %0, %2;" : "+r"(g) : "r"(a), "r"(e));
         asm volatile("mad.hi.s32 %0, %1, %0, %2;" : "+r"(h) : "r"(a), "r"(e)); asm volatile("mad.hi.s32 %0, %1, %0, %2;" : "+r"(i2) : "r"(a), "r"(e)); }
+      if (MODE >= 30 && MODE <= 35) { // the biquad step built up piece by piece: d = sum, f = ys (y << 16), g = y2s, h = res
+        int pre = c, e2 = e;
+        if (MODE >= 33) { // three feed-forward products of a changing input i2
+          i2 = i2 * 1664525 + 1013904223;
+          if (MODE == 35) { // on the FP64 pipe
+            const double xD = __hiloint2double(0x41310000 + (i2 >> 16), 0);
+            e2 = __double2loint(__fma_rd(dm, xD, da)) + __double2loint(__fma_rd(dm, x1, da)) + __double2loint(__fma_rd(dm, x2, da));
+            x2 = x1; x1 = xD;
+          } else {
+            int t0, t1, t2;
+            asm volatile("mul.hi.s32 %0, %1, %2;" : "=r"(t0) : "r"(a), "r"(i2));
+            asm volatile("mul.hi.s32 %0, %1, %2;" : "=r"(t1) : "r"(c), "r"(i2 ^ 0x55));
+            asm volatile("mul.hi.s32 %0, %1, %2;" : "=r"(t2) : "r"(e), "r"(i2 ^ 0x77));
+            e2 = t0 + t1 + t2;
+          }
+        }
+        if (MODE >= 32) asm volatile("mad.hi.s32 %0, %1, %2, %3;" : "=r"(e2) : "r"(c), "r"(g), "r"(e2)); // a2 * y2 + e
+        if (MODE == 31) asm volatile("mad.lo.s32 %0, %1, %2, %3;" : "=r"(pre) : "r"(h), "r"(one), "r"(c));
+        if (MODE >= 32) asm volatile("mad.lo.s32 %0, %1, %2, %3;" : "=r"(pre) : "r"(h), "r"(one), "r"(e2));
+        asm volatile("mad.hi.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(f), "r"(pre)); // sum = a1 * y1 + pre
+        g = f;
+        int sh14;
+        asm volatile("shr.s32 %0, %1, 14;" : "=r"(sh14) : "r"(d));
+        asm volatile("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(f) : "r"(sh14), "r"(zero));
+        if (MODE >= 31) asm volatile("and.b32 %0, %1, 0x3fff;" : "=r"(h) : "r"(d));
+      }
       if (MODE == 11) asm volatile("cvt.sat.s16.s32 %0, %0;" : "+r"(d));
       if (MODE == 12) { long long w; asm volatile("mul.wide.s32 %0, %1, %2;" : "=l"(w) : "r"(a), "r"(d)); d = (int)(w >> 32) + c; }
       if (MODE == 13) asm volatile("mul.hi.s32 %0, %1, %0;" : "+r"(d) : "r"(a));
@@ -106,6 +132,11 @@ int main()
   run<27>("y cycle + 1 independent IMAD.HI", d_cyc, d_sink);
   run<26>("y cycle + 1 independent IMAD.HI + 3 DFMA", d_cyc, d_sink);
   run<28>("y cycle + 4 independent IMAD.HI", d_cyc, d_sink);
+  run<30>("step A: y cycle only (IMAD.HI a1, SHF, I2IP)", d_cyc, d_sink);
+  run<31>("step B: A + residual (LOP3, opaque IMAD)", d_cyc, d_sink);
+  run<32>("step C: B + IMAD.HI a2*y2", d_cyc, d_sink);
+  run<33>("step D: C + 3 feed-forward IMAD.HI (the full step)", d_cyc, d_sink);
+  run<35>("step E: C + 3 feed-forward DFMA (hybrid step)", d_cyc, d_sink);
   printf("cuda status: %s\n", cudaGetErrorString(cudaGetLastError()));
   return 0;
 }
