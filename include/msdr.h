@@ -128,10 +128,12 @@ int msdr_chain_get_state(msdr_chain *chain, uint32_t ch, msdr_channel_state *out
 int msdr_chain_set_state(msdr_chain *chain, uint32_t ch, const msdr_channel_state *in);
 
 /* Options.  "variant" selects the shape of the fused kernel for studies and cross-checks (all shapes are bit-exact):
- *   0    default: tensor-core FIR producers (tcgen05 kind::i8) + pinned biquad chains, post warps where they fit
+ *   0    default: tensor-core FIR producers (tcgen05 kind::i8) + pinned biquad chains; feed-forward helper warps up to 148
+ *        channel groups, two chain sets per SM beyond
  *   64   CUDA-core FIR kernel (msdr_chain_v3.cu); +1: biquad products on the FP64 pipe; +8: two channels per chain lane
- *   128  tensor-core kernel with feed-forward helper warps;  256: tensor-core kernel without post warps;
- *   512  never run two chain sets per SM (the default does for more than 148 channel groups)
+ *   128  helper-warp shape even beyond 148 groups;  2048: post-warp shape (whole stages in the chain warps);
+ *   256  classic shape (neither helper nor post warps)
+ *   512  never run two chain sets per SM
  *   +16 / +32: ablation (skip the FIR / the biquad arithmetic; results are wrong, timing only)
  * "timing" (CUDA events around each update), "host_chunk_channels", "host_chunk_blocks" (msdr_chain_update pipelining).
  * Environment, developer aids: MSDR_VARIANT (default variant of new chains), MSDR_PROF (per-role cycle counters on stderr). */

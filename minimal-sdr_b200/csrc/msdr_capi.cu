@@ -672,7 +672,7 @@ int msdr_chain_update_range_device(msdr_chain *chain, uint32_t ch0, uint32_t nch
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, chain->device));
     // more channel groups than SMs: two chain sets per SM (waves of 2 x SMs groups), unless a study variant asks for a
     // specific shape (bits 7, 8) or forbids it (bit 9)
-    bool dual = NG > (uint32_t)sms && !(chain->variant & (128 | 256 | 512));
+    bool dual = NG > (uint32_t)sms && !(chain->variant & (128 | 256 | 512 | 2048));
     int st = build_tc_plan(chain, ch0, nch, (uint32_t)sms * (dual ? 2u : 1u));
     if (st != MSDR_OK) return st;
     if (dual && chain->plan.usable && !chain->plan.rings[3]) { // the second set of chain slots does not fit next to this window
@@ -688,9 +688,10 @@ int msdr_chain_update_range_device(msdr_chain *chain, uint32_t ch0, uint32_t nch
       p.W = pl.W; // chains per wave
       p.n_items = pl.n_rb * p.NT;
       p.tc_rowmap = pl.d_rowmap; p.tc_rb = pl.d_rb; p.tc_grp = pl.d_grp; p.tc_wave_rb0 = pl.d_wave_rb0; p.tc_bmat = pl.d_bmat;
-      // kernel shape: post warps where they fit, else the plain classic shape; variant bit 7 asks for the FF chain side and
-      // bit 8 for the classic shape without post warps (study knobs)
-      uint32_t shape = pl.rings[0] ? 0u : 1u;
+      // kernel shape: feed-forward helper warps where they fit (shape 2), else post warps (0), else the plain classic shape (1);
+      // variant bits 11 / 8 / 7 ask for the post-warp, the classic and the helper-warp shape (study knobs)
+      uint32_t shape = pl.rings[2] ? 2u : pl.rings[0] ? 0u : 1u;
+      if ((chain->variant & 2048) && pl.rings[0]) shape = 0u;
       if ((chain->variant & 256) && pl.rings[1]) shape = 1u;
       if ((chain->variant & 128) && pl.rings[2]) shape = 2u;
       if (dual) shape = 3u;

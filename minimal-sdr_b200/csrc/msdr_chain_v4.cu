@@ -67,6 +67,7 @@ template <bool FF, bool POST, bool DUAL = false> struct Roles {
   static constexpr int kLive = (4 + 1 + NCONV + NPOST) * 32;
   static constexpr int kLoadWarp = FF ? 10 : 8;  // FF helpers sit on different sub-partitions (2 and 3): each saturates an IMAD.HI pipe for a while
   static constexpr int kMidWarp = FF ? 11 : -1;
+  static constexpr int kRawWarp = FF ? 8 : -1;   // FF: the raw rows are fetched by a warp of their own, FF1 only computes
   // converters wait on memory, not on issue slots: in the classic shape two of them sit next to the chain warps (12, 13)
   static __device__ __forceinline__ bool is_conv(int w)
   {
@@ -103,6 +104,7 @@ struct __align__(16) Ctrl {
   uint64_t tmem_empty;         // epilogue -> MMA  : accumulators drained (4 arrivals)
   uint64_t staged_full[2][4];  // epilogue warp i -> post warp i : packed I/Q rows parked in staging buffer b (classic)
   uint64_t staged_free[2][4];  // post warp i -> epilogue warp i : staging buffer b written back
+  uint64_t raw_full[NSLOT_MAX];  // raw loader -> FF1 (FF only): the sub-tile's cp.async copies have landed (32 arrivals)
   uint64_t ld_full[NSLOT_MAX];   // load -> chain A  : sub-tile in smem
   uint64_t ab_full[NSLOT_MAX];   // chain A -> B (classic) / chain A -> FF2 (FF) : object 1 done
   uint64_t m_full[NSLOT_MAX];    // FF2 -> chain B   : feed-forward sums of object 2 ready (FF only)
@@ -192,6 +194,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
     for (int b = 0; b < 2; ++b)
       for (int i = 0; i < 4; ++i) { mbar_init(&pc->staged_full[b][i], 1); mbar_init(&pc->staged_free[b][i], 1); }
     for (int s = 0; s < NSLOT_MAX; ++s) {
+      mbar_init(&pc->raw_full[s], 32);
       mbar_init(&pc->ld_full[s], 1); mbar_init(&pc->ab_full[s], 1); mbar_init(&pc->m_full[s], 1); mbar_init(&pc->st_full[s], 1); mbar_init(&pc->slot_free[s], 1);
     }
     mbar_fence_init();
@@ -470,15 +473,16 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
           uint32_t *er = slotE(slot), *yr = slotY(slot);
           if (!(p.ablate & 2u) && active) {
             if (fast) {
-              uint4 n0 = *reinterpret_cast<const uint4 *>(er), n1 = *reinterpret_cast<const uint4 *>(er + 4);
+              const uint32_t ea = smem_u32(er), ya = smem_u32(yr);
+              uint4 n0 = lds128(ea), n1 = lds128(ea + 16u);
 #pragma unroll 1
               for (int q = 0; q < SUB_FF / 8; ++q) {
                 const uint4 e0 = n0, e1 = n1;
-                if (q + 1 < SUB_FF / 8) { n0 = *reinterpret_cast<const uint4 *>(er + 8 * q + 8); n1 = *reinterpret_cast<const uint4 *>(er + 8 * q + 12); }
+                if (q + 1 < SUB_FF / 8) { n0 = lds128(ea + 32u * (uint32_t)(q + 1)); n1 = lds128(ea + 32u * (uint32_t)(q + 1) + 16u); }
                 const int y0 = rec_step(rec, (int)e0.x), y1 = rec_step(rec, (int)e0.y), y2 = rec_step(rec, (int)e0.z), y3 = rec_step(rec, (int)e0.w);
                 const int y4 = rec_step(rec, (int)e1.x), y5 = rec_step(rec, (int)e1.y), y6 = rec_step(rec, (int)e1.z), y7 = rec_step(rec, (int)e1.w);
-                *reinterpret_cast<uint4 *>(yr + 4 * q) = make_uint4(__byte_perm((uint32_t)y0, (uint32_t)y1, 0x7632), __byte_perm((uint32_t)y2, (uint32_t)y3, 0x7632),
-                                                                  __byte_perm((uint32_t)y4, (uint32_t)y5, 0x7632), __byte_perm((uint32_t)y6, (uint32_t)y7, 0x7632));
+                sts128(ya + 16u * (uint32_t)q, make_uint4(__byte_perm((uint32_t)y0, (uint32_t)y1, 0x7632), __byte_perm((uint32_t)y2, (uint32_t)y3, 0x7632),
+                                                           __byte_perm((uint32_t)y4, (uint32_t)y5, 0x7632), __byte_perm((uint32_t)y6, (uint32_t)y7, 0x7632)));
               }
             } else { // generic cascade, stage-major like the reference (filter_biquad.cpp:44-79): E holds x << 16, filtered in place
               for (int j = 0; j < nst; ++j) {
@@ -512,45 +516,6 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
         const bool fast = object_fast(obj, ch, active, nst);
         BqFF ff{};
         if (fast && active) bq_load_ff(ff, p.bq, p.Cpad, obj, ch);
-        int ready = 0; // leading units known to be in `out` for every row of the group
-        // all rows of the group have the unit of sub-tile k in `out`?  (blocking or a single poll)
-        auto unit_ready = [&](int k, bool blocking) -> bool {
-          const int need = (k * SUB_FF) / UNIT;
-          while (ready <= need) {
-            int ok = 1;
-            if (lane == 0) {
-              const long long t0 = clock64();
-              while (ld_relaxed_gpu(p.tile_cnt + (size_t)g * p.NU + ready) < nrows) {
-                if (!blocking) { ok = 0; break; }
-                __nanosleep(64);
-                if (clock64() - t0 > kWatchdogCycles) __trap();
-              }
-              if (ok) fence_acquire_gpu();
-            }
-            ok = __shfl_sync(0xffffffffu, ok, 0);
-            if (!ok) return false;
-            ++ready;
-          }
-          return true;
-        };
-        // load side: the raw rows of sub-tile kk go global -> Y rows of its slot with cp.async (no registers, coalesced: 4 rows of
-        // 128 bytes per warp instruction), one sub-tile ahead of the feed-forward pass, so the ~1.3 k-cycle round trip is hidden
-        const int cr0 = lane >> 3, cc = lane & 7;
-        auto issue_rows = [&](int kk, uint32_t pp, bool blocking) -> bool {
-          const int sl = (int)(pp % NSLOT_FF);
-          if (!unit_ready(kk, blocking)) return false;
-          if (blocking) mbar_wait(&pc->slot_free[sl], ((pp / NSLOT_FF) & 1u) ^ 1u);
-          else if (!mbar_test_wait(&pc->slot_free[sl], ((pp / NSLOT_FF) & 1u) ^ 1u)) return false;
-          const unsigned char *gsrc = reinterpret_cast<const unsigned char *>(p.out + ((size_t)g * kGroup + cr0) * p.stride + (size_t)kk * SUB_FF) + cc * 16;
-          const uint32_t sdst = smem_u32(bq_base + (uint32_t)sl * kSlotBytesFF) + (uint32_t)(kGroup * EW + cr0 * YW) * 4u + cc * 16;
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (cr0 + 4 * j < nrows)
-              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst + (uint32_t)j * 4u * YW * 4u), "l"(gsrc + (size_t)j * 4u * p.stride * 2u) : "memory");
-          asm volatile("cp.async.commit_group;" ::: "memory");
-          return true;
-        };
-        bool issued = false; // rows of the current sub-tile already requested
         for (int k = 0; k < nsub; ++k, ++pos) {
           const int slot = (int)(pos % NSLOT_FF);
           const uint32_t phs = (pos / NSLOT_FF) & 1u;
@@ -558,12 +523,8 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
           uint4 v[SUB_FF / 8];
           prof.start();
           if (isLoad) {
-            if (!issued) issue_rows(k, pos, true);
+            mbar_wait(&pc->raw_full[slot], phs); // every lane's copies of this sub-tile have landed (raw loader, warp 8)
             prof.lap(0);
-            issued = (k + 1 < nsub) && issue_rows(k + 1, pos + 1, false);
-            if (issued) asm volatile("cp.async.wait_group 1;" ::: "memory");
-            else asm volatile("cp.async.wait_group 0;" ::: "memory");
-            __syncwarp(); // every lane's copies of this sub-tile have landed
             prof.lap(1);
             const uint32_t *yr = slotY(slot);
             if (active) {
@@ -603,12 +564,63 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
           __syncwarp();
           if (lane == 0) {
             mbar_arrive(isLoad ? &pc->ld_full[slot] : &pc->m_full[slot]);
-            if (isLoad && ((((k + 1) * SUB_FF) % SPAN) == 0 || k + 1 == nsub)) atomicAdd(p.ctrl + 1, 1); // flow control
           }
           prof.lap(2);
         }
         if (fast && active) bq_store_ff(ff, p.bq, p.Cpad, obj, ch);
-        if (isLoad) {
+      }
+      prof.flush();
+    } else if (warp == R::kRawWarp) {
+      // raw loader: the demodulated rows of sub-tile k go `out` -> Y rows of its slot with cp.async (no registers, coalesced: 4 rows
+      // of 128 bytes per warp instruction), as far ahead of the feed-forward pass as the slot ring allows; the copies' completion
+      // arrives on raw_full[slot] (cp.async.mbarrier.arrive.noinc, one arrival per lane)
+      uint32_t pos = 0;
+      for (int g = (int)blockIdx.x; g < (int)p.NG; g += (int)p.W) {
+        const int nrows = min(kGroup, (int)p.C - g * kGroup);
+        int ready = 0; // leading units known to be in `out` for every row of the group
+        // all rows of the group have the unit of sub-tile k in `out`?  (blocking or a single poll)
+        auto unit_ready = [&](int k, bool blocking) -> bool {
+          const int need = (k * SUB_FF) / UNIT;
+          while (ready <= need) {
+            int ok = 1;
+            if (lane == 0) {
+              const long long t0 = clock64();
+              while (ld_relaxed_gpu(p.tile_cnt + (size_t)g * p.NU + ready) < nrows) {
+                if (!blocking) { ok = 0; break; }
+                __nanosleep(64);
+                if (clock64() - t0 > kWatchdogCycles) __trap();
+              }
+              if (ok) fence_acquire_gpu();
+            }
+            ok = __shfl_sync(0xffffffffu, ok, 0);
+            if (!ok) return false;
+            ++ready;
+          }
+          return true;
+        };
+        // load side: the raw rows of sub-tile kk go global -> Y rows of its slot with cp.async (no registers, coalesced: 4 rows of
+        // 128 bytes per warp instruction), one sub-tile ahead of the feed-forward pass, so the ~1.3 k-cycle round trip is hidden
+        const int cr0 = lane >> 3, cc = lane & 7;
+        auto issue_rows = [&](int kk, uint32_t pp, bool blocking) -> bool {
+          const int sl = (int)(pp % NSLOT_FF);
+          if (!unit_ready(kk, blocking)) return false;
+          if (blocking) mbar_wait(&pc->slot_free[sl], ((pp / NSLOT_FF) & 1u) ^ 1u);
+          else if (!mbar_test_wait(&pc->slot_free[sl], ((pp / NSLOT_FF) & 1u) ^ 1u)) return false;
+          const unsigned char *gsrc = reinterpret_cast<const unsigned char *>(p.out + ((size_t)g * kGroup + cr0) * p.stride + (size_t)kk * SUB_FF) + cc * 16;
+          const uint32_t sdst = smem_u32(bq_base + (uint32_t)sl * kSlotBytesFF) + (uint32_t)(kGroup * EW + cr0 * YW) * 4u + cc * 16;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (cr0 + 4 * j < nrows)
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst + (uint32_t)j * 4u * YW * 4u), "l"(gsrc + (size_t)j * 4u * p.stride * 2u) : "memory");
+          asm volatile("cp.async.commit_group;" ::: "memory");
+          return true;
+        };
+        for (int k = 0; k < nsub; ++k, ++pos) {
+          issue_rows(k, pos, true);
+          asm volatile("cp.async.mbarrier.arrive.noinc.shared.b64 [%0];" ::"r"(smem_u32(&pc->raw_full[pos % NSLOT_FF])) : "memory");
+          if (lane == 0 && ((((k + 1) * SUB_FF) % SPAN) == 0 || k + 1 == nsub)) atomicAdd(p.ctrl + 1, 1); // flow control: span taken
+        }
+        {
           // carry the last H raw samples: hist <- tail of (hist || in[0..L)).  Every unit of this group has been counted and
           // only a span's first window reaches back into the history, so nobody reads the old history any more.
           const uint32_t hq = p.H >> 3; // uint4 per history row (<= 33)
@@ -633,7 +645,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
           }
         }
       }
-      prof.flush();
+      asm volatile("cp.async.wait_all;" ::: "memory");
     } else if (warp == kStoreWarp) {
       // final audio: Y rows -> `out`, 4 rows of 128 bytes per warp instruction
       Prof prof(p.prof, 6);

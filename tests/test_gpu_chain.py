@@ -298,8 +298,9 @@ def test_update_range_device(msdr, orc, K):
     assert_same(d_out.cpu().numpy(), yo, "range update")
 
 
-@pytest.mark.parametrize("variant,name", [(0, "tensor-core FIR + post warps"), (256, "tensor-core FIR, inline epilogue"),
-                                            (128, "tensor-core FIR, feed-forward helper warps"), (64, "CUDA-core FIR (v3)"), (65, "v3, FP64 biquad")])
+@pytest.mark.parametrize("variant,name", [(0, "default (tensor-core FIR, feed-forward helper warps)"), (2048, "tensor-core FIR + post warps"),
+                                            (256, "tensor-core FIR, inline epilogue"), (128, "helper warps, forced"), (64, "CUDA-core FIR (v3)"),
+                                            (65, "v3, FP64 biquad")])
 def test_every_kernel_shape_is_bit_exact(msdr, orc, K, variant, name):
     """All shapes of the fused kernel (option "variant") produce the oracle's bits: mixed modes, ragged updates, 4-stage cascades on
     some channels, full-range (wrapping) taps on others, extreme inputs, a partial last group."""
