@@ -388,7 +388,7 @@ def main():
                          "peak_source": peak_src, "kernel": "msdr::v4::chain_kernel (fused mix + tensor-core FIR pair + demod + biquad cascade)",
                          "algorithmic_bytes_per_sample": ALGO_BYTES_PER_SAMPLE, "samples_per_launch": samples_per_launch,
                          "avg_launch_ms": per_launch_s * 1e3, "recurrence": recurrence,
-                         "note": "not HBM-bound: 4096 channels are 128 biquad chains, each an exact-arithmetic serial recurrence of ~47 cycles per sample per warp; the FIR pair runs beside them on the tensor cores (tcgen05 kind::i8); see DESIGN.md section 6"},
+                         "note": "not HBM-bound: 4096 channels are 128 biquad chains, each an exact-arithmetic serial recurrence (34 cycles per sample in the recurrence warps, feed-forward products in helper warps); the FIR pair runs beside them on the tensor cores (tcgen05 kind::i8); see DESIGN.md section 6"},
             "e2e": e2e,
         }
         if world == 1 and not args.no_cpu:

@@ -56,9 +56,10 @@ constexpr int kThreads = 16 * 32;
 //   DUAL     classic without post warps, but TWO chain sets per SM (load 12 -> A 10 -> B 11 -> store 13 is the second): for more
 //            channel groups than SMs, where one chain pair per SM is the ceiling (~170 Gsamples/s); 3 convert warps (7,14,15)
 //   FF       the three input-side products of a stage do not depend on its output, so they are taken off the chain warps:
-//            load+FF1 (warp 10) -> A -> FF2 (warp 11) -> B -> store.  Warps 10/11 (sub-partitions 2, 3) hand the chain warps the
-//            feed-forward sums e[n] as 32-bit words and A/B run only the two recurrence products per sample
-//            (tools/microbench/bqstep2.cu: 35 instead of 45 cycles per step).  3 convert warps (7,14,15).
+//            raw loader (warp 8) -> FF1 (warp 10) -> A -> FF2 (warp 11) -> B -> store.  Warps 10/11 (sub-partitions 2, 3) hand the
+//            chain warps the feed-forward sums e[n] as 32-bit words and A/B run only the two recurrence products per sample
+//            (tools/microbench/lat.cu: 24 instead of 38 cycles per step isolated).  3 convert warps (7,14,15).  The default
+//            up to one channel group per SM.
 template <bool FF, bool POST, bool DUAL = false> struct Roles {
   static_assert(!(FF && POST) && !(DUAL && (FF || POST)), "shapes are exclusive: every warp has one role");
   static constexpr int NCONV = (FF || POST || DUAL) ? 3 : 5;
@@ -867,9 +868,9 @@ uint32_t chain_v4_span_samples() { return v4::SPAN; }
 uint32_t chain_v4_unit_samples() { return v4::UNIT; }
 
 // Shapes of the fused kernel for window K, each with the deepest operand ring (at least one pair ahead of the window) that fits:
-//   shape 0  classic chain side + post warps (two staging buffers)     -- the default where it fits
+//   shape 0  classic chain side + post warps (two staging buffers)     -- the default where shape 2 does not fit
 //   shape 1  classic chain side, epilogue warps demodulate themselves  -- long windows (256 taps)
-//   shape 2  FF chain side                                             -- opt-in (variant bit 7)
+//   shape 2  FF chain side (feed-forward helper warps)                 -- the default up to one channel group per SM
 //   shape 3  two chain sets per SM, no post warps                      -- more channel groups than SMs
 // rings[s] = 0: shape s does not fit.  false = the tensor-core form does not apply at all.
 bool chain_v4_config(uint32_t K, int smem_max, uint32_t rings[4])
