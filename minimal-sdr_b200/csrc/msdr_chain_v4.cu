@@ -58,11 +58,11 @@ constexpr int kThreads = 16 * 32;
 //   FF       the three input-side products of a stage do not depend on its output, so they are taken off the chain warps:
 //            raw loader (warp 8) -> FF1 (warp 10) -> A -> FF2 (warp 11) -> B -> store.  Warps 10/11 (sub-partitions 2, 3) hand the
 //            chain warps the feed-forward sums e[n] as 32-bit words and A/B run only the two recurrence products per sample
-//            (tools/microbench/lat.cu: 24 instead of 38 cycles per step isolated).  3 convert warps (7,14,15).  The default
+//            (tools/microbench/lat.cu: 24 instead of 38 cycles per step isolated).  5 convert warps (7,12,13,14,15).  The default
 //            up to one channel group per SM.
 template <bool FF, bool POST, bool DUAL = false> struct Roles {
   static_assert(!(FF && POST) && !(DUAL && (FF || POST)), "shapes are exclusive: every warp has one role");
-  static constexpr int NCONV = (FF || POST || DUAL) ? 3 : 5;
+  static constexpr int NCONV = FF ? 5 : (POST || DUAL) ? 3 : 5;
   static constexpr int NPOST = POST ? 4 : 0;     // warps 10,11,14,15 take demodulation + write-back off the epilogue warps
   static constexpr int NSTAGE = POST ? 2 : 1;    // staging buffers between epilogue and post warps
   static constexpr int kLive = (4 + 1 + NCONV + NPOST) * 32;
@@ -72,11 +72,11 @@ template <bool FF, bool POST, bool DUAL = false> struct Roles {
   // converters wait on memory, not on issue slots: in the classic shape two of them sit next to the chain warps (12, 13)
   static __device__ __forceinline__ bool is_conv(int w)
   {
-    return (FF || DUAL) ? (w == 7 || w == 14 || w == 15) : POST ? (w == 7 || w == 12 || w == 13) : (w == 7 || w == 10 || w == 11 || w == 14 || w == 15);
+    return FF ? (w == 7 || w == 12 || w == 13 || w == 14 || w == 15) : DUAL ? (w == 7 || w == 14 || w == 15) : POST ? (w == 7 || w == 12 || w == 13) : (w == 7 || w == 10 || w == 11 || w == 14 || w == 15);
   }
   static __device__ __forceinline__ int conv_index(int w)
   {
-    return (FF || DUAL) ? (w == 7 ? 0 : w == 14 ? 1 : 2) : POST ? (w == 7 ? 0 : w == 12 ? 1 : 2) : (w == 7 ? 0 : w == 10 ? 1 : w == 11 ? 2 : w == 14 ? 3 : 4);
+    return FF ? (w == 7 ? 0 : w == 12 ? 1 : w == 13 ? 2 : w == 14 ? 3 : 4) : DUAL ? (w == 7 ? 0 : w == 14 ? 1 : 2) : POST ? (w == 7 ? 0 : w == 12 ? 1 : 2) : (w == 7 ? 0 : w == 10 ? 1 : w == 11 ? 2 : w == 14 ? 3 : 4);
   }
   // classic chain side: which chain set (0, or 1 in the DUAL shape) and which role (0 load, 1 A, 2 B, 3 store) a warp has
   static __device__ __forceinline__ void chain_role(int w, int &set, int &role)
