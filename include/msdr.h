@@ -95,6 +95,9 @@ int msdr_fir_init_q15(msdr_chain *chain, uint32_t ch0, uint32_t nch, uint16_t nu
 /* In-place rewrite of the bound tables (calc_demod_filter(), Minimal-SDR.ino:221-223 / UI.cpp:337-345): same tap
  * count, delay lines kept.  All channels in the range must currently share one table. */
 int msdr_fir_set_coefficients(msdr_chain *chain, uint32_t ch0, uint32_t nch, const int16_t *cI, const int16_t *cQ);
+/* numTaps of the FIR pair bound to channel `ch` (arm_fir_instance_q15::numTaps, arm_math.h:1027-1032): what
+ * msdr_fir_set_coefficients reads from cI and cQ.  0 = not initialised; negative = bad argument. */
+int msdr_chain_fir_taps(const msdr_chain *chain, uint32_t ch);
 
 /* AudioFilterBiquad::setCoefficients(stage, const int *) (filter_biquad.cpp:84-100) on object `object`
  * (0 = biquad1_dac, 1 = biquad2_dac): coef = {b0,b1,b2,a1,a2} in Q2.30; a1,a2 are stored negated; the previous
@@ -121,6 +124,13 @@ int msdr_chain_update_range_device(msdr_chain *chain, uint32_t ch0, uint32_t nch
 /* Device time of the last update in milliseconds (CUDA events), the analogue of the reference's
  * micros()-around-demodulation() load figure (Minimal-SDR.ino:533,774; :415-432). Synchronises. */
 int msdr_chain_last_update_ms(msdr_chain *chain, float *ms);
+/* AudioProcessorUsage() / AudioProcessorUsageMax() / AudioProcessorUsageMaxReset() of the Teensy core as the sketch uses them
+ * (Minimal-SDR.ino:424-426: load as a percentage of the block period AUDIO_BLOCK_SAMPLES / pdb_freq_actual): device time of an
+ * update divided by the real-time duration of the blocks it processed at `sample_rate_hz`, for the last update and as a
+ * running maximum.  The first call switches the "timing" option on (updates before it are not counted); reading the figures
+ * waits for the last update to finish. */
+int msdr_chain_processor_usage(msdr_chain *chain, double sample_rate_hz, float *last_percent, float *max_percent);
+int msdr_chain_processor_usage_max_reset(msdr_chain *chain);
 /* Number of kernels launched by this chain since creation (bench.py reports it as gpu_launches). */
 uint64_t msdr_chain_launch_count(const msdr_chain *chain);
 

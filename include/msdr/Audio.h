@@ -16,6 +16,9 @@
 //   AudioFilterBiquad::setCoefficients/setLowpass…  same signatures (filter_biquad.h:43-149); update() = msdr_op_biquad, or a
 //                                                   no-op pass-through when the object is bound to a Receiver (fused kernel)
 //   AudioEffectFreqConv::direction/passthrough      same (freq_conv.h:36-56); update() = msdr_op_freq_conv
+//   AudioFilterFIR::begin(coeffs, n)/end()          same (the Teensy Audio library's filter_fir.h, which the reference lists at
+//                                                   src/Audio/Audio.h:96 but does not vendor); update() = msdr_op_fir_fast_q15
+//   AudioProcessorUsageMax()/…MaxReset()            same (Minimal-SDR.ino:424-426); fed by the Receivers' device time per block
 //   arm_fir_init_q15 + arm_fir_fast_q15 (x2),       Receiver::init_FIR / tune / demodulation(): ONE fused launch for the whole
 //     mix loop, demod switch in demodulation()        batch, including the two biquad objects that follow queue_dac
 //
@@ -396,6 +399,53 @@ private:
   bool dir, pass;
 };
 
+// ---- AudioFilterFIR: the Teensy Audio library's FIR object (filter_fir.h; listed at src/Audio/Audio.h:96, not vendored by the
+// reference).  Call shape from the library's documentation: begin(coefficients, count) binds a q15 table (borrowed pointer,
+// like arm_fir_init_q15.c:103) and zeroes the delay line; FIR_PASSTHRU forwards blocks unchanged; end() or a failed init (odd
+// count, arm_fir_init_q15.c:93-96; more than FIR_MAX_COEFFS) leaves the object without coefficients and it then consumes its
+// input and transmits nothing.  update() is arm_fir_fast_q15 (arm_fir_fast_q15.c:60-329) on every channel of the batch block.
+#ifndef FIR_MAX_COEFFS
+#define FIR_MAX_COEFFS 200
+#endif
+#define FIR_PASSTHRU ((const short *)1)
+class AudioFilterFIR : public AudioStream {
+public:
+  AudioFilterFIR(void) : AudioStream(1, inputQueueArray), coeff_p(nullptr), n_coeffs(0) {}
+  void begin(const short *cp, int n)
+  {
+    coeff_p = cp;
+    n_coeffs = n;
+    history.clear(); // arm_fir_init_q15 zeroes pState
+    if (coeff_p && coeff_p != FIR_PASSTHRU && (n > FIR_MAX_COEFFS || n < 2 || (n & 1))) coeff_p = nullptr;
+  }
+  void end(void) { coeff_p = nullptr; }
+  int device = 0;
+  int last_status() const { return status_; }
+  virtual void update(void)
+  {
+    audio_block_t *block = receiveReadOnly();
+    if (!block) return;
+    if (!coeff_p) { release(block); return; }
+    if (coeff_p == FIR_PASSTHRU) { transmit(block); release(block); return; }
+    audio_block_t *b_new = allocate();
+    if (b_new) {
+      const size_t hn = (size_t)block->channels * (size_t)(n_coeffs - 1);
+      if (history.size() != hn) history.assign(hn, 0);
+      status_ = msdr_op_fir_fast_q15(device, (uint16_t)n_coeffs, coeff_p, history.data(), block->data, b_new->data, block->channels,
+                                     AUDIO_BLOCK_SAMPLES, AUDIO_BLOCK_SAMPLES);
+      transmit(b_new);
+      release(b_new);
+    }
+    release(block);
+  }
+private:
+  const short *coeff_p;
+  int n_coeffs;
+  std::vector<int16_t> history; // [channels][n_coeffs - 1]: the head of each channel's pState (arm_fir_fast_q15.c:296-327)
+  audio_block_t *inputQueueArray[1];
+  int status_ = 0;
+};
+
 // ---- AudioAmplifier (mixer.{h,cpp}): the sketch's amp_adc / amp_dac ---------------------------------------------------------
 class AudioAmplifier : public AudioStream {
 public:
@@ -455,8 +505,16 @@ public:
   Receiver(uint32_t n_channels, int device = 0, uint32_t max_taps = 0, uint32_t flags = 0) : n_(n_channels)
   {
     status_ = msdr_chain_create(&chain_, device, n_channels, max_taps, flags);
+    live().push_back(this);
   }
-  ~Receiver() { msdr_chain_destroy(chain_); }
+  ~Receiver()
+  {
+    auto &r = live();
+    for (size_t i = 0; i < r.size(); ++i)
+      if (r[i] == this) { r.erase(r.begin() + (long)i); break; }
+    msdr_chain_destroy(chain_);
+  }
+  static std::vector<Receiver *> &live() { static std::vector<Receiver *> r; return r; }
   Receiver(const Receiver &) = delete;
   Receiver &operator=(const Receiver &) = delete;
   bool ok() const { return chain_ != nullptr; }
@@ -517,6 +575,29 @@ private:
   uint32_t n_;
   int status_;
 };
+
+// AudioProcessorUsageMax() / AudioProcessorUsageMaxReset() / AudioProcessorUsage() of the Teensy core, as the sketch prints them
+// (Minimal-SDR.ino:424-426): processing time as a percentage of the block period.  Here: the largest figure over the live
+// Receivers, each = device time of an update / real-time duration of its blocks at AudioProcessorUsageSampleRate() (the
+// sketch's pdb_freq_actual; default AUDIO_SAMPLE_RATE_EXACT).  Counting starts with the first call.
+inline double &AudioProcessorUsageSampleRate() { static double fs = AUDIO_SAMPLE_RATE_EXACT; return fs; }
+inline float AudioProcessorUsage_(bool want_max)
+{
+  float best = 0.0f;
+  for (Receiver *r : Receiver::live()) {
+    float last = 0.0f, mx = 0.0f;
+    if (r->ok() && msdr_chain_processor_usage(r->handle(), AudioProcessorUsageSampleRate(), &last, &mx) == MSDR_OK)
+      best = std::fmax(best, want_max ? mx : last);
+  }
+  return best;
+}
+inline float AudioProcessorUsage() { return AudioProcessorUsage_(false); }
+inline float AudioProcessorUsageMax() { return AudioProcessorUsage_(true); }
+inline void AudioProcessorUsageMaxReset()
+{
+  for (Receiver *r : Receiver::live())
+    if (r->ok()) msdr_chain_processor_usage_max_reset(r->handle());
+}
 
 inline void AudioFilterBiquad::setCoefficients(uint32_t stage, const int *coefficients)
 {

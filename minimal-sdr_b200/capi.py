@@ -63,6 +63,9 @@ SYMBOLS = {
     "msdr_chain_set_mode": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int]),
     "msdr_fir_init_q15": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint16, C.c_void_p, C.c_void_p]),
     "msdr_fir_set_coefficients": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "msdr_chain_fir_taps": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "msdr_chain_processor_usage": (C.c_int, [C.c_void_p, C.c_double, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "msdr_chain_processor_usage_max_reset": (C.c_int, [C.c_void_p]),
     "msdr_biquad_set_coefficients": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]),
     "msdr_chain_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_size_t]),
     "msdr_chain_update_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_size_t]),

@@ -72,10 +72,17 @@ class ReceiveChain:
         st = self._L.msdr_fir_init_q15(self.h, ch0, nch, cI.size, capi.ptr(cI), capi.ptr(cQ))
         return self._ck(st) if check else st
 
+    def fir_taps(self, ch=0):
+        """numTaps of the FIR pair bound to channel ch (0 = not initialised)."""
+        return int(self._L.msdr_chain_fir_taps(self.h, int(ch)))
+
     def fir_set_coefficients(self, cI, cQ, ch0=0, nch=None):
         ch0, nch = self._rng(ch0, nch)
         cI = np.ascontiguousarray(cI, np.int16)
         cQ = np.ascontiguousarray(cQ, np.int16)
+        T = self.fir_taps(ch0)  # the C ABI reads the bound tap count from both arrays, like the reference's borrowed pointer
+        if T > 0 and not (cI.size == cQ.size == T):
+            raise capi.MsdrError(capi.ERR_LENGTH, f"fir_set_coefficients: {cI.size}/{cQ.size} taps given, {T} bound")
         return self._ck(self._L.msdr_fir_set_coefficients(self.h, ch0, nch, capi.ptr(cI), capi.ptr(cQ)))
 
     def tables_for_mode(self, mode, am_table=None):
@@ -169,6 +176,15 @@ class ReceiveChain:
         ms = C.c_float(0)
         self._ck(self._L.msdr_chain_last_update_ms(self.h, C.byref(ms)))
         return ms.value
+
+    def processor_usage(self, sample_rate_hz):
+        """(last, max) load in percent of the block period at sample_rate_hz: AudioProcessorUsage / AudioProcessorUsageMax."""
+        a, b = C.c_float(0), C.c_float(0)
+        self._ck(self._L.msdr_chain_processor_usage(self.h, float(sample_rate_hz), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def processor_usage_max_reset(self):
+        return self._ck(self._L.msdr_chain_processor_usage_max_reset(self.h))
 
     def launch_count(self):
         return int(self._L.msdr_chain_launch_count(self.h))

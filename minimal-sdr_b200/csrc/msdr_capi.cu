@@ -67,6 +67,11 @@ struct msdr_chain {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::vector<cudaEvent_t> pipe_ev;
   bool timed = false;
+  // processor usage (AudioProcessorUsage / AudioProcessorUsageMax of the Teensy core, Minimal-SDR.ino:424-426): device time of an
+  // update per 128-sample block, last and running maximum; `usage_pending` = events of the last timed update not read back yet
+  bool usage_pending = false;
+  uint32_t usage_blocks = 0;
+  float usage_last_ms_per_block = 0.f, usage_max_ms_per_block = 0.f;
 
   std::vector<uint8_t> h_mode, h_set; // h_set: 0xFF = FIR not initialised
   uint32_t n_uninit = 0;
@@ -93,8 +98,8 @@ struct msdr_chain {
   uint64_t meta_version = 1;  // bumped whenever a channel's table binding or a table's contents change
   struct TcPlan {
     uint64_t version = 0;
-    uint32_t ch0 = 0, nch = 0, W = 0, K = 0, rings[4] = {0, 0, 0, 0}, n_rb = 0, n_waves = 0;
-    bool usable = false;
+    uint32_t ch0 = 0, nch = 0, sms = 0, W = 0, K = 0, rings[4] = {0, 0, 0, 0}, n_rb = 0, n_waves = 0;
+    bool usable = false, want_dual = false, dual = false;
     uint32_t *d_rowmap = nullptr, *d_grp = nullptr, *d_wave_rb0 = nullptr;
     uint4 *d_rb = nullptr;
     uint8_t *d_bmat = nullptr;
@@ -147,6 +152,19 @@ int cuda_fail(msdr_chain *c, cudaError_t e, const char *what)
   } while (0)
 
 bool range_ok(const msdr_chain *c, uint32_t ch0, uint32_t nch) { return (uint64_t)ch0 + nch <= c->C; }
+
+// read back the events of the last timed update (blocks until it has finished) and fold it into the usage figures
+int usage_resolve(msdr_chain *chain)
+{
+  if (!chain->usage_pending) return MSDR_OK;
+  chain->usage_pending = false;
+  float ms = 0.f;
+  CK(cudaEventSynchronize(chain->ev1));
+  CK(cudaEventElapsedTime(&ms, chain->ev0, chain->ev1));
+  chain->usage_last_ms_per_block = ms / (float)std::max(1u, chain->usage_blocks);
+  chain->usage_max_ms_per_block = std::max(chain->usage_max_ms_per_block, chain->usage_last_ms_per_block);
+  return MSDR_OK;
+}
 
 int upload_set(msdr_chain *chain, uint32_t id)
 {
@@ -326,6 +344,12 @@ int msdr_chain_synchronize(msdr_chain *chain)
 const char *msdr_last_error(const msdr_chain *chain) { return chain ? chain->err.c_str() : g_create_error.c_str(); }
 uint32_t msdr_chain_channels(const msdr_chain *chain) { return chain ? chain->C : 0; }
 uint64_t msdr_chain_launch_count(const msdr_chain *chain) { return chain ? chain->launches : 0; }
+int msdr_chain_fir_taps(const msdr_chain *chain, uint32_t ch)
+{
+  if (!chain || ch >= chain->C) return MSDR_ERR_ARGUMENT;
+  const uint8_t sid = chain->h_set[ch];
+  return sid == 0xFF ? 0 : (int)chain->sets[sid].T;
+}
 
 int msdr_chain_set_mode(msdr_chain *chain, uint32_t ch0, uint32_t nch, int mode)
 {
@@ -402,6 +426,19 @@ int msdr_fir_init_q15(msdr_chain *chain, uint32_t ch0, uint32_t nch, uint16_t nu
   if (numTaps < 4 || numTaps > chain->max_taps) return fail(chain, MSDR_ERR_LENGTH, "fir_init: numTaps outside [4, max_taps of this chain]");
   if (nch == 0) return MSDR_OK;
   CK(cudaSetDevice(chain->device));
+  // a table used by nobody but this range is about to lose its last user: give its slot back first, so re-tuning a full chain
+  // (MSDR_MAX_FIR_SETS live tables) does not fail for want of the slot it is freeing itself
+  {
+    uint32_t in_range[MSDR_MAX_FIR_SETS] = {0};
+    for (uint32_t c = ch0; c < ch0 + nch; ++c)
+      if (chain->h_set[c] != 0xFF) in_range[chain->h_set[c]]++;
+    for (uint32_t sid = 0; sid < chain->sets.size(); ++sid)
+      if (in_range[sid] && in_range[sid] == chain->sets[sid].users) {
+        for (uint32_t c = ch0; c < ch0 + nch; ++c)
+          if (chain->h_set[c] == sid) { chain->h_set[c] = 0xFF; chain->n_uninit++; }
+        chain->sets[sid].users = 0;
+      }
+  }
   const int id = intern_set(chain, numTaps, cI, cQ);
   if (id < 0) return id;
   int st = assign_set(chain, ch0, nch, (uint32_t)id);
@@ -456,13 +493,16 @@ void free_tc_plan(msdr_chain *chain)
 // inside each wave the rows are sorted by table and cut into blocks of 128 (the last block of a table is padded).
 // Every block lists the channel groups it contributes to and with how many rows: the epilogue adds those counts to
 // tile_cnt[group][span], a chain starts a span when the count reaches the group's row count.
-int build_tc_plan(msdr_chain *chain, uint32_t ch0, uint32_t nch, uint32_t W)
+// want_dual: the caller would like waves of 2 x sms chains (two chain sets per SM); the plan is built with that width only if the
+// window leaves room for the second set of chain slots (rings[3]), which is known before any row is sorted — so the wave width
+// is chosen once and an unchanged configuration always hits the cache (256 taps beyond 148 groups used to rebuild twice per update).
+int build_tc_plan(msdr_chain *chain, uint32_t ch0, uint32_t nch, uint32_t sms, bool want_dual)
 {
   msdr_chain::TcPlan &pl = chain->plan;
-  if (pl.version == chain->meta_version && pl.ch0 == ch0 && pl.nch == nch && pl.W == W) return MSDR_OK;
+  if (pl.version == chain->meta_version && pl.ch0 == ch0 && pl.nch == nch && pl.sms == sms && pl.want_dual == want_dual) return MSDR_OK;
   CK(cudaStreamSynchronize(chain->stream)); // a launch in flight may still read the old plan
   free_tc_plan(chain);
-  pl.version = chain->meta_version; pl.ch0 = ch0; pl.nch = nch; pl.W = W;
+  pl.version = chain->meta_version; pl.ch0 = ch0; pl.nch = nch; pl.sms = sms; pl.want_dual = want_dual;
 
   uint32_t kp_max = 0;
   for (uint32_t c = ch0; c < ch0 + nch; ++c) kp_max = std::max(kp_max, kp_of_taps(chain->sets[chain->h_set[c]].T));
@@ -471,6 +511,8 @@ int build_tc_plan(msdr_chain *chain, uint32_t ch0, uint32_t nch, uint32_t W)
   CK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, chain->device));
   if (!chain_v4_config(K, smem_max, pl.rings)) { pl.usable = false; return MSDR_OK; }
   pl.K = K;
+  pl.dual = want_dual && pl.rings[3] != 0;
+  const uint32_t W = pl.W = sms * (pl.dual ? 2u : 1u);
 
   const uint32_t NG = (nch + kGroup - 1) / kGroup, n_sets = (uint32_t)chain->sets.size(), M = tc_tile_rows();
   std::vector<uint32_t> rowmap, grp, wave_rb0;
@@ -672,15 +714,11 @@ int msdr_chain_update_range_device(msdr_chain *chain, uint32_t ch0, uint32_t nch
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, chain->device));
     // more channel groups than SMs: two chain sets per SM (waves of 2 x SMs groups), unless a study variant asks for a
     // specific shape (bits 7, 8) or forbids it (bit 9)
-    bool dual = NG > (uint32_t)sms && !(chain->variant & (128 | 256 | 512 | 2048));
-    int st = build_tc_plan(chain, ch0, nch, (uint32_t)sms * (dual ? 2u : 1u));
+    const bool want_dual = NG > (uint32_t)sms && !(chain->variant & (128 | 256 | 512 | 2048));
+    int st = build_tc_plan(chain, ch0, nch, (uint32_t)sms, want_dual);
     if (st != MSDR_OK) return st;
-    if (dual && chain->plan.usable && !chain->plan.rings[3]) { // the second set of chain slots does not fit next to this window
-      dual = false;
-      st = build_tc_plan(chain, ch0, nch, (uint32_t)sms);
-      if (st != MSDR_OK) return st;
-    }
     const msdr_chain::TcPlan &pl = chain->plan;
+    const bool dual = pl.dual; // false when the second set of chain slots does not fit next to this window (256 taps)
     use_tc = pl.usable;
     if (use_tc) {
       p.NG = NG;
@@ -709,7 +747,11 @@ int msdr_chain_update_range_device(msdr_chain *chain, uint32_t ch0, uint32_t nch
       p.tile_cnt = chain->d_tile_cnt;
     }
   }
-  if (chain->timed) CK(cudaEventRecord(chain->ev0, chain->stream));
+  if (chain->timed) {
+    int stu = usage_resolve(chain); // the event pair is reused: fold the previous update in first
+    if (stu != MSDR_OK) return stu;
+    CK(cudaEventRecord(chain->ev0, chain->stream));
+  }
   {
     int stl = syncam_lane_prepare(chain, ch0, nch, d_in, stride, p.L);
     if (stl != MSDR_OK) return stl;
@@ -727,7 +769,11 @@ int msdr_chain_update_range_device(msdr_chain *chain, uint32_t ch0, uint32_t nch
     int stl = syncam_lane_finish(chain, ch0, d_out, stride, p.L);
     if (stl != MSDR_OK) return stl;
   }
-  if (chain->timed) CK(cudaEventRecord(chain->ev1, chain->stream));
+  if (chain->timed) {
+    CK(cudaEventRecord(chain->ev1, chain->stream));
+    chain->usage_pending = true;
+    chain->usage_blocks = n_blocks;
+  }
   chain->launches++;
   if (d_prof) {
     std::vector<long long> h((size_t)p.W * 64);
@@ -818,6 +864,28 @@ int msdr_chain_last_update_ms(msdr_chain *chain, float *ms)
   CK(cudaEventSynchronize(chain->ev1));
   CK(cudaEventElapsedTime(ms, chain->ev0, chain->ev1));
   return MSDR_OK;
+}
+
+int msdr_chain_processor_usage(msdr_chain *chain, double sample_rate_hz, float *last_percent, float *max_percent)
+{
+  if (!chain || !(sample_rate_hz > 0.0)) return MSDR_ERR_ARGUMENT;
+  CK(cudaSetDevice(chain->device));
+  chain->timed = true; // from now on every update is bracketed by events
+  int st = usage_resolve(chain);
+  if (st != MSDR_OK) return st;
+  const double block_ms = 1e3 * MSDR_BLOCK_SAMPLES / sample_rate_hz; // the real-time budget of one block (Minimal-SDR.ino:425)
+  if (last_percent) *last_percent = (float)(100.0 * chain->usage_last_ms_per_block / block_ms);
+  if (max_percent) *max_percent = (float)(100.0 * chain->usage_max_ms_per_block / block_ms);
+  return MSDR_OK;
+}
+
+int msdr_chain_processor_usage_max_reset(msdr_chain *chain)
+{
+  if (!chain) return MSDR_ERR_ARGUMENT;
+  CK(cudaSetDevice(chain->device));
+  int st = usage_resolve(chain);
+  chain->usage_max_ms_per_block = 0.f;
+  return st;
 }
 
 int msdr_chain_set_option(msdr_chain *chain, const char *key, int value)

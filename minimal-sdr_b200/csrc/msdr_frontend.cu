@@ -346,6 +346,12 @@ int msdr_frontend_get_state(msdr_frontend *fe, uint32_t ch, msdr_frontend_state 
 int msdr_frontend_set_state(msdr_frontend *fe, uint32_t ch, const msdr_frontend_state *in)
 {
   if (!fe || !in || ch >= fe->C) return MSDR_ERR_ARGUMENT;
+  // agc_idx indexes the 25-entry block-maximum history after a pre-decrement (Minimal-SDR.ino:481): the sketch only ever holds
+  // 0..25 there; anything else (a corrupt or foreign checkpoint) would be an out-of-bounds store in the kernel
+  if (in->agc_idx < 0 || in->agc_idx > msdr::fe::kAgcBuf) {
+    fe->err = "frontend_set_state: agc_idx outside [0, 25]";
+    return MSDR_ERR_ARGUMENT;
+  }
   FCK(cudaSetDevice(fe->device));
   FCK(cudaStreamSynchronize(fe->stream));
   FCK(cudaMemcpy(fe->d_state + ch, in, sizeof(*in), cudaMemcpyHostToDevice));

@@ -19,8 +19,35 @@ from conftest import adversarial_inputs, wrap_coeffs  # noqa: E402
 import minimal_sdr_b200 as m  # noqa: E402
 
 
+def freq_conv_inputs():
+    """A6 known-answer inputs: every pairing of the q15 corner values (saturation of the products' sum / difference, the
+    -32768 * -32768 product that overflows q15) plus seeded full-range noise, against fs/4 tables and full-scale noise tables."""
+    rng = np.random.default_rng(606)
+    corners = np.array([-32768, -32767, -16384, -1, 0, 1, 16384, 32766, 32767], np.int16)
+    g = np.array(np.meshgrid(corners, corners, corners, corners, indexing="ij")).reshape(4, -1)  # I, Q, oscI, oscQ: 6561 columns
+    n = (g.shape[1] + 127) // 128 * 128 + 128 * 8
+    I, Q, oI, oQ = (rng.integers(-32768, 32768, n, dtype=np.int16) for _ in range(4))
+    I[:g.shape[1]], Q[:g.shape[1]], oI[:g.shape[1]], oQ[:g.shape[1]] = g
+    k = np.arange(128 * 4)
+    oI[-512:] = np.array([0, 32767, 0, -32767], np.int16)[k % 4]   # the fs/4 oscillator a user of the class would supply
+    oQ[-512:] = np.array([32767, 0, -32767, 0], np.int16)[k % 4]
+    return I, Q, oI, oQ
+
+
+def freq_conv_kat(ref):
+    I, Q, oI, oQ = freq_conv_inputs()
+    kat = {"I": I, "Q": Q, "oscI": oI, "oscQ": oQ}
+    for d in (0, 1):
+        for ps in (0, 1):
+            kat[f"I_dir{d}_pass{ps}"], kat[f"Q_dir{d}_pass{ps}"] = ref.freq_conv(d, ps, I, Q, oI, oQ)
+    np.savez_compressed(os.path.join(HERE, "freqconv_kat.npz"), **kat)
+
+
 def main():
     ref = ol.CheckerLib("ref")
+    freq_conv_kat(ref)
+    if "--only-freqconv" in sys.argv:
+        return
     K = m.load_ref_constants()
     rng = np.random.default_rng(20261017)
     tabs = {

@@ -16,7 +16,12 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 ORACLE_SO = os.path.join(ORACLE_DIR, "libmsdr_oracle.so")
-REF_SO = os.path.join(ORACLE_DIR, "_ref", "libmsdr_ref.so")
+REF_SO = os.environ.get("MSDR_REF_SO") or os.path.join(ORACLE_DIR, "_ref", "libmsdr_ref.so")  # env: test another build of the same sources
+# builds of the reference sources at other optimisation levels (oracle/Makefile `ref_variants`): CPU-baseline timing and a
+# cross-check that the compiled reference does not depend on the optimiser
+REF_VARIANTS = {"O2": REF_SO,
+                "O2-novec": os.path.join(ORACLE_DIR, "_ref", "o2novec", "libmsdr_ref.so"),
+                "O3-x86-64-v3": os.path.join(ORACLE_DIR, "_ref", "o3", "libmsdr_ref.so")}
 
 MODE_SYNCAM, MODE_AM, MODE_LSB, MODE_USB, MODE_CW = 0, 1, 2, 3, 4  # stations.h:4
 DEMOD_LSB, DEMOD_USB, DEMOD_AM_F32, DEMOD_AM_Q31 = 0, 1, 2, 3
@@ -46,12 +51,14 @@ def have_ref():
 class CheckerLib:
     """Uniform view of either checker library."""
 
-    def __init__(self, prefix):
+    def __init__(self, prefix, path=None):
         assert prefix in ("orc", "ref")
         self.prefix = prefix
         if prefix == "orc":
             _ensure(ORACLE_SO, "libmsdr_oracle.so")
             self.lib = C.CDLL(ORACLE_SO)
+        elif path:  # another build of the same reference sources (REF_VARIANTS)
+            self.lib = C.CDLL(path)
         else:
             if not have_ref():
                 raise FileNotFoundError(REF_SO)
@@ -85,6 +92,14 @@ class CheckerLib:
             bind("biquad_design", None, [C.c_void_p, C.c_int, C.c_uint32, C.c_float, C.c_float, C.c_float])
             bind("calc_FIR_coeffs", None, [_i16p, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float])
             bind("audio_sample_rate_exact", C.c_double, [])
+            try:  # A6: the reference's own freq_conv.cpp + the vendored saturating primitives (oracle/ref_freq_conv.cpp, ref_q15_prims.c)
+                bind("freq_conv", None, [C.c_int, C.c_int, _i16p, _i16p, _i16p, _i16p, C.c_uint32])
+                bind("freq_conv_ex", C.c_int, [C.c_int, C.c_int, _i16p, _i16p, _i16p, _i16p, C.c_uint32, C.c_int, C.c_int, C.c_int])
+                bind("qadd16", C.c_uint32, [C.c_uint32, C.c_uint32])
+                bind("qsub16", C.c_uint32, [C.c_uint32, C.c_uint32])
+                bind("clip_q31_to_q15", C.c_int16, [C.c_int32])
+            except AttributeError:  # a _ref library built before these were added
+                pass
         bind("chain_new", C.c_void_p, [C.c_uint32, C.c_int])
         bind("chain_free", None, [C.c_void_p])
         bind("chain_set_mode", C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int])
@@ -165,6 +180,14 @@ class CheckerLib:
         self._f["freq_conv"](int(direction), int(passthrough), I, Q,
                              np.ascontiguousarray(oscI, np.int16), np.ascontiguousarray(oscQ, np.int16), I.size)
         return I, Q
+
+    def freq_conv_ex(self, direction, passthrough, I, Q, oscI, oscQ, have_I=1, have_Q=1, fail_alloc=0):
+        """compiled reference only: (I, Q, transmitted) with a missing input block or a failed allocate()"""
+        I = np.ascontiguousarray(I, np.int16).copy()
+        Q = np.ascontiguousarray(Q, np.int16).copy()
+        ok = self._f["freq_conv_ex"](int(direction), int(passthrough), I, Q, np.ascontiguousarray(oscI, np.int16),
+                                     np.ascontiguousarray(oscQ, np.int16), I.size, have_I, have_Q, fail_alloc)
+        return I, Q, bool(ok)
 
     def biquad_design(self, kind, frequency, p2, p3=1.0, stage=0):
         h = self._f["biquad_new"]()

@@ -101,3 +101,28 @@ def test_frontend_objects(msdr, tmp_path):
         for c in range(C):
             exp, sent = forc.amp_apply(x[c, b * 128:(b + 1) * 128], forc.amp_multiplier(gain))
             assert np.array_equal(oamp[c, b * 128:(b + 1) * 128], exp), (c, b)
+
+
+def test_fir_object_and_processor_usage(msdr, orc, K, tmp_path):
+    """AudioFilterFIR::begin/end/update in an AudioConnection graph (arm_fir_fast_q15 per channel, FIR_PASSTHRU, end(), failed init) and
+    AudioProcessorUsageMax()/AudioProcessorUsageMaxReset() fed by a Receiver (Minimal-SDR.ino:424-426); host/fir_usage_objects.cpp."""
+    _build()
+    C, NB = 6, 9
+    rng = np.random.default_rng(33)
+    x = rng.integers(-32768, 32768, (C, NB * 128), dtype=np.int16)
+    x[1] = -32768
+    taps = np.array(K["FIR_SSB_I_coeffs"], np.int16)
+    with open(tmp_path / "taps.bin", "wb") as f:
+        f.write(np.int32(taps.size).tobytes() + taps.tobytes())
+    x.tofile(tmp_path / "in.bin")
+    r = subprocess.run([os.path.join(HOST, "fir_usage_objects"), str(C), str(NB), str(tmp_path / "taps.bin"), str(tmp_path / "in.bin"),
+                        str(tmp_path / "out.bin"), str(tmp_path / "sent.bin")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    y = np.fromfile(tmp_path / "out.bin", np.int16).reshape(C, NB * 128)
+    sent = np.fromfile(tmp_path / "sent.bin", np.uint8)
+    assert sent.tolist() == [1, 1, 1, 0, 1, 0, 1, 1, 1]  # end() and the odd tap count transmit nothing; FIR_PASSTHRU forwards
+    for c in range(C):
+        assert np.array_equal(y[c, :3 * 128], orc.fir(taps, x[c, :3 * 128])), c
+        assert np.array_equal(y[c, 4 * 128:5 * 128], x[c, 4 * 128:5 * 128]), c
+        assert np.array_equal(y[c, 6 * 128:], orc.fir(taps, x[c, 6 * 128:])), c  # begin() zeroed the delay line
+    assert "usage before 0.0000%" in r.stdout

@@ -146,3 +146,17 @@ def test_freq_conv(msdr, orc):
                 for r in range(5):
                     a, b = orc.freq_conv(d, ps, I[r], Q[r], oi, oq)
                     assert np.array_equal(i2[r], a) and np.array_equal(q2[r], b), (d, ps, r)
+
+
+def test_freq_conv_reference_known_answers(msdr):
+    """A6 against tests/golden/freqconv_kat.npz — outputs of the reference's own freq_conv.cpp (compiled with arm_mult/add/sub_q15
+    built from the vendored saturating primitives, oracle/ref_q15_prims.c) on every pairing of the q15 corner values."""
+    import os
+    L, p = msdr.capi.lib(), msdr.capi.ptr
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "freqconv_kat.npz"))
+    n = z["I"].size
+    for d in (0, 1):
+        for ps in (0, 1):
+            i2, q2 = z["I"].copy(), z["Q"].copy()
+            assert L.msdr_op_freq_conv(0, d, ps, p(i2), p(q2), p(z["oscI"]), p(z["oscQ"]), 1, n, n) == 0
+            assert np.array_equal(i2, z[f"I_dir{d}_pass{ps}"]) and np.array_equal(q2, z[f"Q_dir{d}_pass{ps}"]), (d, ps)

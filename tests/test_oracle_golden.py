@@ -91,3 +91,12 @@ def test_freq_conv_semantics(orc):
     i2, q2 = orc.freq_conv(1, 1, I, Q, oscI, oscQ)
     assert np.array_equal(q2, np.clip(a(Q, oscQ) + a(I, oscI), -32768, 32767).astype(np.int16))
     assert np.array_equal(i2, np.clip(a(I, oscQ) - a(Q, oscI), -32768, 32767).astype(np.int16))
+
+
+def test_freq_conv_golden(orc):
+    """A6 known answers generated from the reference's own freq_conv.cpp (tests/golden/make_golden.py::freq_conv_kat)."""
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "freqconv_kat.npz"))
+    for d in (0, 1):
+        for ps in (0, 1):
+            i, q = orc.freq_conv(d, ps, z["I"], z["Q"], z["oscI"], z["oscQ"])
+            assert np.array_equal(i, z[f"I_dir{d}_pass{ps}"]) and np.array_equal(q, z[f"Q_dir{d}_pass{ps}"]), (d, ps)

@@ -118,3 +118,72 @@ def test_chain_matches_reference(orc, ref, K, am_q31):
         ch.close()
     assert np.array_equal(ys[0], ys[1])
     assert np.abs(ys[0][:4].astype(np.int32)).max() > 100  # the chain actually passes signal
+
+
+def test_reference_builds_agree_across_optimisation_levels(orc, K):
+    """oracle/Makefile `ref_variants`: the reference sources at -O2 (default), -O2 -fno-tree-vectorize and -O3 -march=x86-64-v3 give
+    the same chain output as the oracle on wrap / saturation inputs, so the faster build is a valid CPU baseline (bench.py)."""
+    import os
+    from chain_helpers import tables_for
+    rng = np.random.default_rng(77)
+    modes = [ol.MODE_AM, ol.MODE_USB, ol.MODE_LSB, ol.MODE_CW, ol.MODE_AM, ol.MODE_USB]
+    x = np.stack([v for v in list(adversarial_inputs(128 * 6, rng).values())[:6]])
+    tabs = {1: (wrap_coeffs(86, rng), wrap_coeffs(86, rng)), 4: (wrap_coeffs(102, rng), wrap_coeffs(102, rng))}
+
+    def run(lib):
+        o = lib.chain(len(modes))
+        for c, md in enumerate(modes):
+            o.set_mode(c, 1, md)
+            assert o.fir_init(c, 1, *(tabs.get(c) or tables_for(K, md))) == 0
+        o.biquad_set_coefficients(0, 0, len(modes), 0, K["biquad1_lowpass_coef"])
+        o.biquad_set_coefficients(1, 0, len(modes), 0, K["biquad2_notch_coef"])
+        y = o.run(x)[0]
+        o.close()
+        return y
+
+    want = run(orc)
+    seen = 0
+    for name, path in ol.REF_VARIANTS.items():
+        if not os.path.exists(path):
+            continue
+        assert np.array_equal(run(ol.CheckerLib("ref", path=path)), want), name
+        seen += 1
+    if seen == 0:
+        pytest.skip("no oracle/_ref build here")
+
+
+def test_freq_conv_matches_reference_class(orc, ref):
+    """A6: orc_freq_conv == the reference's own freq_conv.cpp compiled where it lies, with arm_mult/add/sub_q15 built from the
+    vendored portable clip_q31_to_q15 / __QADD16 / __QSUB16 (arm_math.h:555-560,721-765): every pairing of the q15 corner values
+    (sum / difference saturation, -32768 * -32768), both directions, both pass settings."""
+    if "freq_conv" not in ref._f:
+        pytest.skip("oracle/_ref predates the freq_conv build")
+    sys_path_golden = __import__("os").path.join(__import__("os").path.dirname(__file__), "golden")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", __import__("os").path.join(sys_path_golden, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    I, Q, oI, oQ = mg.freq_conv_inputs()
+    for d in (0, 1):
+        for ps in (0, 1):
+            a, b = orc.freq_conv(d, ps, I, Q, oI, oQ), ref.freq_conv(d, ps, I, Q, oI, oQ)
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), (d, ps)
+    # silent-drop paths of the class (freq_conv.cpp:40-47,64,111): nothing is transmitted
+    assert ref.freq_conv_ex(0, 1, I[:128], Q[:128], oI[:128], oQ[:128], have_I=0)[2] is False
+    assert ref.freq_conv_ex(0, 1, I[:128], Q[:128], oI[:128], oQ[:128], have_Q=0)[2] is False
+    assert ref.freq_conv_ex(0, 1, I[:128], Q[:128], oI[:128], oQ[:128], fail_alloc=1)[2] is False
+    assert ref.freq_conv_ex(0, 1, I[:128], Q[:128], oI[:128], oQ[:128])[2] is True
+
+
+def test_vendored_saturating_primitives(ref):
+    """The saturating q15 primitives the reference vendors (portable C, arm_math.h:555-560,721-765), on their corners."""
+    if "qadd16" not in ref._f:
+        pytest.skip("oracle/_ref predates the freq_conv build")
+    f = ref._f
+    pk = lambda hi, lo: ((hi & 0xFFFF) << 16) | (lo & 0xFFFF)
+    assert f["qadd16"](pk(32767, -32768), pk(1, -1)) == pk(32767, -32768)      # both lanes saturate
+    assert f["qadd16"](pk(-1, 5), pk(1, -5)) == pk(0, 0)
+    assert f["qsub16"](pk(-32768, 32767), pk(1, -1)) == pk(-32768, 32767)
+    assert f["qsub16"](pk(0, 0), pk(-32768, -32768)) == pk(32767, 32767)      # 0 - (-32768) saturates
+    assert f["clip_q31_to_q15"]((-32768 * -32768) >> 15) == 32767              # the one q15 product that overflows
+    assert f["clip_q31_to_q15"](-32769) == -32768 and f["clip_q31_to_q15"](12345) == 12345
