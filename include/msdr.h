@@ -92,6 +92,10 @@ int msdr_chain_set_mode(msdr_chain *chain, uint32_t ch0, uint32_t nch, int mode)
  * "time reversed" order (arm_fir_init_q15.c:50-54).  Odd numTaps -> MSDR_ERR_ARGUMENT and nothing changes. */
 int msdr_fir_init_q15(msdr_chain *chain, uint32_t ch0, uint32_t nch, uint16_t numTaps, const int16_t *cI, const int16_t *cQ);
 
+/* The same two setters for a list of channels (n entries, any order): configures interleaved mode families with one call each. */
+int msdr_chain_set_mode_list(msdr_chain *chain, const uint32_t *channels, uint32_t n, int mode);
+int msdr_fir_init_q15_list(msdr_chain *chain, const uint32_t *channels, uint32_t n, uint16_t numTaps, const int16_t *cI, const int16_t *cQ);
+
 /* In-place rewrite of the bound tables (calc_demod_filter(), Minimal-SDR.ino:221-223 / UI.cpp:337-345): same tap
  * count, delay lines kept.  All channels in the range must currently share one table. */
 int msdr_fir_set_coefficients(msdr_chain *chain, uint32_t ch0, uint32_t nch, const int16_t *cI, const int16_t *cQ);
@@ -133,6 +137,11 @@ int msdr_chain_processor_usage(msdr_chain *chain, double sample_rate_hz, float *
 int msdr_chain_processor_usage_max_reset(msdr_chain *chain);
 /* Number of kernels launched by this chain since creation (bench.py reports it as gpu_launches). */
 uint64_t msdr_chain_launch_count(const msdr_chain *chain);
+/* How often the row plan of the tensor-core kernel (channels sorted by tap table, Toeplitz operands) was rebuilt: once per
+ * change of a table binding, a table's contents or the updated channel range - never per update of an unchanged configuration. */
+uint64_t msdr_chain_plan_build_count(const msdr_chain *chain);
+/* Which fused kernel (and which of its shapes) the last update launched; bench.py names it in `roofline.kernel`. */
+const char *msdr_chain_last_kernel(const msdr_chain *chain);
 
 int msdr_chain_get_state(msdr_chain *chain, uint32_t ch, msdr_channel_state *out);
 int msdr_chain_set_state(msdr_chain *chain, uint32_t ch, const msdr_channel_state *in);

@@ -8,11 +8,11 @@ call fails if no GPU is present — there is no CPU fallback.
 
 The directory name contains a hyphen, so import it through the `minimal_sdr_b200` shim at the repo root.
 """
-from . import anr, capi, chain, design, frontend, shard, syncam, synth  # noqa: F401
+from . import anr, capi, chain, design, frontend, shard, syncam, synth, workloads  # noqa: F401
 from .capi import MsdrError, lib_path  # noqa: F401
 from .chain import ReceiveChain, load_ref_constants  # noqa: F401
 from .anr import Anr  # noqa: F401
 from .frontend import Frontend  # noqa: F401
 from .syncam import SyncAm  # noqa: F401
 
-__all__ = ["anr", "Anr", "capi", "chain", "design", "frontend", "shard", "syncam", "synth", "ReceiveChain", "Frontend", "SyncAm", "MsdrError", "lib_path", "load_ref_constants"]
+__all__ = ["anr", "Anr", "capi", "chain", "design", "frontend", "shard", "syncam", "synth", "workloads", "ReceiveChain", "Frontend", "SyncAm", "MsdrError", "lib_path", "load_ref_constants"]

@@ -63,6 +63,8 @@ SYMBOLS = {
     "msdr_chain_set_mode": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int]),
     "msdr_fir_init_q15": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint16, C.c_void_p, C.c_void_p]),
     "msdr_fir_set_coefficients": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "msdr_chain_set_mode_list": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int]),
+    "msdr_fir_init_q15_list": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint16, C.c_void_p, C.c_void_p]),
     "msdr_chain_fir_taps": (C.c_int, [C.c_void_p, C.c_uint32]),
     "msdr_chain_processor_usage": (C.c_int, [C.c_void_p, C.c_double, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "msdr_chain_processor_usage_max_reset": (C.c_int, [C.c_void_p]),
@@ -72,6 +74,8 @@ SYMBOLS = {
     "msdr_chain_update_range_device": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_size_t]),
     "msdr_chain_last_update_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "msdr_chain_launch_count": (C.c_uint64, [C.c_void_p]),
+    "msdr_chain_plan_build_count": (C.c_uint64, [C.c_void_p]),
+    "msdr_chain_last_kernel": (C.c_char_p, [C.c_void_p]),
     "msdr_chain_get_state": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(ChannelState)]),
     "msdr_chain_set_state": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(ChannelState)]),
     "msdr_chain_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),

@@ -72,6 +72,17 @@ class ReceiveChain:
         st = self._L.msdr_fir_init_q15(self.h, ch0, nch, cI.size, capi.ptr(cI), capi.ptr(cQ))
         return self._ck(st) if check else st
 
+    def set_mode_list(self, mode, channels):
+        ch = np.ascontiguousarray(channels, np.uint32)
+        return self._ck(self._L.msdr_chain_set_mode_list(self.h, capi.ptr(ch), ch.size, int(mode)))
+
+    def fir_init_list(self, cI, cQ, channels):
+        ch = np.ascontiguousarray(channels, np.uint32)
+        cI = np.ascontiguousarray(cI, np.int16)
+        cQ = np.ascontiguousarray(cQ, np.int16)
+        assert cI.size == cQ.size
+        return self._ck(self._L.msdr_fir_init_q15_list(self.h, capi.ptr(ch), ch.size, cI.size, capi.ptr(cI), capi.ptr(cQ)))
+
     def fir_taps(self, ch=0):
         """numTaps of the FIR pair bound to channel ch (0 = not initialised)."""
         return int(self._L.msdr_chain_fir_taps(self.h, int(ch)))
@@ -185,6 +196,12 @@ class ReceiveChain:
 
     def processor_usage_max_reset(self):
         return self._ck(self._L.msdr_chain_processor_usage_max_reset(self.h))
+
+    def plan_build_count(self):
+        return int(self._L.msdr_chain_plan_build_count(self.h))
+
+    def last_kernel(self):
+        return (self._L.msdr_chain_last_kernel(self.h) or b"").decode()
 
     def launch_count(self):
         return int(self._L.msdr_chain_launch_count(self.h))

@@ -132,6 +132,8 @@ struct msdr_chain {
   uint64_t launches = 0;
   std::string err;
   ChainLaunchInfo last_info{};
+  std::string last_kernel = "none";
+  uint64_t plan_builds = 0;
 };
 
 namespace {
@@ -344,6 +346,8 @@ int msdr_chain_synchronize(msdr_chain *chain)
 const char *msdr_last_error(const msdr_chain *chain) { return chain ? chain->err.c_str() : g_create_error.c_str(); }
 uint32_t msdr_chain_channels(const msdr_chain *chain) { return chain ? chain->C : 0; }
 uint64_t msdr_chain_launch_count(const msdr_chain *chain) { return chain ? chain->launches : 0; }
+uint64_t msdr_chain_plan_build_count(const msdr_chain *chain) { return chain ? chain->plan_builds : 0; }
+const char *msdr_chain_last_kernel(const msdr_chain *chain) { return chain ? chain->last_kernel.c_str() : ""; }
 int msdr_chain_fir_taps(const msdr_chain *chain, uint32_t ch)
 {
   if (!chain || ch >= chain->C) return MSDR_ERR_ARGUMENT;
@@ -447,6 +451,64 @@ int msdr_fir_init_q15(msdr_chain *chain, uint32_t ch0, uint32_t nch, uint16_t nu
   return MSDR_OK;
 }
 
+// ---- the same two setters for a LIST of channels: a batch of receivers whose modes interleave (mode = f(channel mod 4) in the
+// benchmark layouts) is configured with one call per mode instead of one per channel
+int msdr_chain_set_mode_list(msdr_chain *chain, const uint32_t *channels, uint32_t n, int mode)
+{
+  if (!chain) return MSDR_ERR_ARGUMENT;
+  if ((!channels && n) || mode < 0 || mode > 4) return fail(chain, MSDR_ERR_ARGUMENT, "set_mode_list: bad arguments");
+  if (n == 0) return MSDR_OK;
+  uint32_t lo = 0xFFFFFFFFu, hi = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    if (channels[i] >= chain->C) return fail(chain, MSDR_ERR_ARGUMENT, "set_mode_list: channel out of range");
+    lo = std::min(lo, channels[i]); hi = std::max(hi, channels[i]);
+  }
+  CK(cudaSetDevice(chain->device));
+  for (uint32_t i = 0; i < n; ++i) chain->h_mode[channels[i]] = (uint8_t)mode;
+  chain->pll.dirty = true;
+  CK(cudaMemcpyAsync(chain->d_mode + lo, chain->h_mode.data() + lo, hi - lo + 1, cudaMemcpyHostToDevice, chain->stream));
+  CK(cudaStreamSynchronize(chain->stream));
+  return MSDR_OK;
+}
+
+int msdr_fir_init_q15_list(msdr_chain *chain, const uint32_t *channels, uint32_t n, uint16_t numTaps, const int16_t *cI, const int16_t *cQ)
+{
+  if (!chain) return MSDR_ERR_ARGUMENT;
+  if (numTaps & 1u) return fail(chain, MSDR_ERR_ARGUMENT, "arm_fir_init_q15: numTaps must be even (arm_fir_init_q15.c:93-96)");
+  if (!cI || !cQ || (!channels && n)) return fail(chain, MSDR_ERR_ARGUMENT, "fir_init_list: bad arguments");
+  if (numTaps < 4 || numTaps > chain->max_taps) return fail(chain, MSDR_ERR_LENGTH, "fir_init: numTaps outside [4, max_taps of this chain]");
+  if (n == 0) return MSDR_OK;
+  uint32_t lo = 0xFFFFFFFFu, hi = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    if (channels[i] >= chain->C) return fail(chain, MSDR_ERR_ARGUMENT, "fir_init_list: channel out of range");
+    lo = std::min(lo, channels[i]); hi = std::max(hi, channels[i]);
+  }
+  CK(cudaSetDevice(chain->device));
+  const int id = intern_set(chain, numTaps, cI, cQ);
+  if (id < 0) return id;
+  uint32_t added = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    const uint32_t c = channels[i];
+    const uint8_t old = chain->h_set[c];
+    if (old == (uint8_t)id) continue; // listed twice, or already bound to this table
+    if (old == 0xFF) chain->n_uninit--; else chain->sets[old].users--;
+    chain->h_set[c] = (uint8_t)id;
+    ++added;
+  }
+  chain->sets[id].users += added;
+  chain->meta_version++;
+  uint32_t *d_list = nullptr;
+  CK(cudaMemcpyAsync(chain->d_set + lo, chain->h_set.data() + lo, hi - lo + 1, cudaMemcpyHostToDevice, chain->stream));
+  CK(cudaMalloc(&d_list, (size_t)n * 4));
+  cudaError_t e = cudaMemcpyAsync(d_list, channels, (size_t)n * 4, cudaMemcpyHostToDevice, chain->stream);
+  if (e == cudaSuccess) e = launch_zero_hist_rows(chain->d_hist, chain->H, d_list, n, chain->stream); // init_FIR memset, .ino:902-903
+  if (e == cudaSuccess) e = cudaStreamSynchronize(chain->stream);
+  cudaFree(d_list);
+  if (e != cudaSuccess) return cuda_fail(chain, e, "fir_init_list");
+  chain->launches++;
+  return MSDR_OK;
+}
+
 int msdr_fir_set_coefficients(msdr_chain *chain, uint32_t ch0, uint32_t nch, const int16_t *cI, const int16_t *cQ)
 {
   if (!chain) return MSDR_ERR_ARGUMENT;
@@ -502,6 +564,7 @@ int build_tc_plan(msdr_chain *chain, uint32_t ch0, uint32_t nch, uint32_t sms, b
   if (pl.version == chain->meta_version && pl.ch0 == ch0 && pl.nch == nch && pl.sms == sms && pl.want_dual == want_dual) return MSDR_OK;
   CK(cudaStreamSynchronize(chain->stream)); // a launch in flight may still read the old plan
   free_tc_plan(chain);
+  chain->plan_builds++;
   pl.version = chain->meta_version; pl.ch0 = ch0; pl.nch = nch; pl.sms = sms; pl.want_dual = want_dual;
 
   uint32_t kp_max = 0;
@@ -763,8 +826,14 @@ int msdr_chain_update_range_device(msdr_chain *chain, uint32_t ch0, uint32_t nch
     CK(cudaMemsetAsync(d_prof, 0, (size_t)p.W * 64 * sizeof(long long), chain->stream));
     p.prof = d_prof;
   }
-  if (use_tc) CK(launch_chain_v4(p, chain->stream, chain->variant, &chain->last_info));
-  else CK(launch_chain(p, chain->stream, chain->variant, &chain->last_info));
+  if (use_tc) {
+    CK(launch_chain_v4(p, chain->stream, chain->variant, &chain->last_info));
+    static const char *shape_name[4] = {"post-warp shape", "classic shape", "feed-forward helper-warp shape", "two chain sets per SM"};
+    chain->last_kernel = std::string("msdr::v4::chain_kernel (fused mix + tensor-core FIR pair + demod + biquad cascade; ") + shape_name[p.tc_ff & 3u] + ")";
+  } else {
+    CK(launch_chain(p, chain->stream, chain->variant, &chain->last_info));
+    chain->last_kernel = "msdr::v3::chain_kernel (fused chain, CUDA-core FIR)";
+  }
   {
     int stl = syncam_lane_finish(chain, ch0, d_out, stride, p.L);
     if (stl != MSDR_OK) return stl;

@@ -78,6 +78,7 @@ cudaError_t launch_demod(int kind, const int16_t *I, const int16_t *Q, int16_t *
 cudaError_t launch_gather_rows(const uint32_t *rows, uint32_t n, uint32_t ch0, const int16_t *hist, uint32_t H, const int16_t *in, size_t stride, int16_t *raw,
                                uint32_t L, cudaStream_t s);
 cudaError_t launch_scatter_rows(const uint32_t *rows, uint32_t n, const int16_t *audio, size_t astride, int16_t *out, size_t stride, uint32_t L, cudaStream_t s);
+cudaError_t launch_zero_hist_rows(int16_t *hist, uint32_t H, const uint32_t *channels, uint32_t n, cudaStream_t s);
 cudaError_t launch_bq_words(int dir, const uint32_t *rows, uint32_t n, uint32_t ch0, int32_t *bq, uint32_t Cpad, int32_t *defs, cudaStream_t s);
 cudaError_t launch_demod_rows(const uint8_t *kinds, const int16_t *I, const int16_t *Q, size_t stride, int16_t *out, size_t ostride, uint32_t rows, uint32_t n,
                               cudaStream_t s);

@@ -361,6 +361,20 @@ cudaError_t launch_scatter_rows(const uint32_t *rows, uint32_t n, const int16_t 
     scatter_rows_kernel<<<dim3(8, std::min(n - r0, 32768u)), 256, 0, s>>>(rows + r0, audio + (size_t)r0 * astride, astride, out, stride, L);
   return cudaGetLastError();
 }
+// zero the raw-sample history rows of a list of channels (init_FIR's memset of both delay lines, Minimal-SDR.ino:902-903)
+__global__ void zero_hist_rows_kernel(int16_t *__restrict__ hist, uint32_t H, const uint32_t *__restrict__ channels, uint32_t n)
+{
+  const uint32_t hq = H / 8; // uint4 per row
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < (size_t)n * hq; i += (size_t)gridDim.x * blockDim.x)
+    reinterpret_cast<uint4 *>(hist + (size_t)channels[i / hq] * H)[i % hq] = make_uint4(0, 0, 0, 0);
+}
+cudaError_t launch_zero_hist_rows(int16_t *hist, uint32_t H, const uint32_t *channels, uint32_t n, cudaStream_t s)
+{
+  if (n == 0) return cudaSuccess;
+  const size_t total = (size_t)n * (H / 8);
+  zero_hist_rows_kernel<<<(unsigned)std::min<size_t>((total + 255) / 256, 148 * 16), 256, 0, s>>>(hist, H, channels, n);
+  return cudaGetLastError();
+}
 cudaError_t launch_bq_words(int dir, const uint32_t *rows, uint32_t n, uint32_t ch0, int32_t *bq, uint32_t Cpad, int32_t *defs, cudaStream_t s)
 {
   if (n == 0) return cudaSuccess;

@@ -73,3 +73,41 @@ def gather_rows(local_rows, shard, total_channels, device=None):
     parts = [torch.empty_like(raw) for _ in shards]
     dist.all_gather(parts, raw)
     return torch.cat([p.view(local_rows.dtype)[:s.n] for p, s in zip(parts, shards)], dim=0)
+
+
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        cpus.update(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa(local_rank):
+    """Pin this process (and so its pinned-buffer pages, which are allocated on first touch, and its copy-issuing thread) to the
+    CPUs of the NUMA node its GPU hangs off.  Eight ranks that all sit on node 0 push every host<->device byte of the other
+    socket's GPUs through the inter-socket link; this is the host-side half of "one process per GPU".  Returns what was done."""
+    import os
+    info = {"node": None, "cpus": None, "bound": False}
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        info["pci"] = bdf
+        info["node"] = node
+        if node < 0:
+            return info
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = _parse_cpulist(f.read())
+        allowed = os.sched_getaffinity(0)
+        use = (cpus & allowed) or None
+        if use:
+            os.sched_setaffinity(0, use)
+            info.update(cpus=len(use), bound=True, allowed_before=len(allowed))
+    except Exception as e:  # no sysfs / not permitted: run unbound and say so
+        info["error"] = f"{type(e).__name__}: {e}"
+    return info

@@ -138,3 +138,134 @@ def test_c5_channel_count(msdr, orc, K):
     g3.update_device(xs.data_ptr(), y3.data_ptr(), nb, xs.stride(0))
     torch.cuda.synchronize()
     assert torch.equal(y3, y[c0:c0 + n])
+
+
+def _checker_for(msdr, lib, w, chans, ch0=0):
+    modes = w.modes(max(chans) + 1, ch0)
+    o = lib.chain(len(chans))
+    for i, c in enumerate(chans):
+        o.set_mode(i, 1, modes[c])
+        assert o.fir_init(i, 1, *w.tables_for(modes[c])) == 0
+    o.biquad_set_coefficients(0, 0, len(chans), 0, w.biquad1)
+    o.biquad_set_coefficients(1, 0, len(chans), 0, w.biquad2)
+    return o
+
+
+def _best_checker(orc):
+    return ol.CheckerLib("ref") if ol.have_ref() else orc
+
+
+def test_c3_benchmarked_launch_shape(msdr, orc, K):
+    """The shape bench.py times: 4096 channels, ONE update of 1024 blocks (131 072 samples per channel, 256 spans — far beyond the
+    producers' flow-control window), then a second update of 64 blocks carrying the state; 48 sampled channels incl. group and tile
+    edges against the compiled reference (oracle/_ref), bit for bit."""
+    import torch
+    w = msdr.workloads.get("c3", K)
+    C = w.channels
+    dev = torch.device("cuda:0")
+    g = msdr.ReceiveChain(C, max_taps=w.max_taps)
+    w.configure(g)
+    g.set_stream(torch.cuda.current_stream().cuda_stream)
+    chans = msdr.workloads.sample_channels(C)
+    o = _checker_for(msdr, _best_checker(orc), w, chans)
+    idx = torch.tensor(chans, device=dev)
+    n0 = 0
+    for nb in (1024, 64):
+        x = msdr.synth.torch_batch(C, nb * 128, dev, w.fs, n0=n0)
+        y = torch.empty_like(x)
+        g.update_device(x.data_ptr(), y.data_ptr(), nb, x.stride(0))
+        torch.cuda.synchronize()
+        assert_same(y[idx].cpu().numpy(), o.run(np.ascontiguousarray(x[idx].cpu().numpy()))[0], f"C3, update of {nb} blocks")
+        assert int(y[idx].abs().max()) > 1000
+        n0 += nb * 128
+    assert g.plan_build_count() == 1
+
+
+def test_c4_at_size_fused_chain(msdr, orc, K):
+    """BASELINE config 4 at size through the FUSED chain: 16 384 channels (512 groups: more than two per SM), 256 taps (255 + the zero
+    arm_fir_init_q15 asks for, arm_fir_init_q15.c:55-64), 192 kHz, updates of 64 + 32 blocks with state carried; sampled channels
+    against the compiled reference.  Also: an unchanged configuration builds its row plan once (the 256-tap window used to rebuild it
+    twice per update)."""
+    import torch
+    w = msdr.workloads.get("c4", K)
+    C = w.channels
+    dev = torch.device("cuda:0")
+    g = msdr.ReceiveChain(C, max_taps=w.max_taps)
+    w.configure(g)
+    assert g.fir_taps(0) == 256 and g.fir_taps(1) == 256
+    g.set_stream(torch.cuda.current_stream().cuda_stream)
+    chans = msdr.workloads.sample_channels(C)
+    o = _checker_for(msdr, _best_checker(orc), w, chans)
+    idx = torch.tensor(chans, device=dev)
+    n0 = 0
+    for nb in (64, 32, 32):
+        x = msdr.synth.torch_batch(C, nb * 128, dev, w.fs, n0=n0)
+        x[3] = -32768                       # two sampled rows made adversarial: the fs/4 negation corner ...
+        x[33, ::2] = 32767                  # ... and full-scale alternation into the long taps
+        y = torch.empty_like(x)
+        g.update_device(x.data_ptr(), y.data_ptr(), nb, x.stride(0))
+        torch.cuda.synchronize()
+        assert_same(y[idx].cpu().numpy(), o.run(np.ascontiguousarray(x[idx].cpu().numpy()))[0], f"C4, update of {nb} blocks")
+        n0 += nb * 128
+    assert int(y[idx].abs().max()) > 300
+    assert g.plan_build_count() == 1, "an unchanged configuration must not rebuild the row plan"
+
+
+def test_c5_interleaved_modes_list_setters(msdr, orc, K):
+    """BASELINE config 5's layout as the benchmark runs it: 2^20 channels with mode = {AM,USB,LSB,CW}[c mod 4] (configured with the
+    list setters, one call per mode), streamed in three updates of 8 blocks with state carried; sampled channels against the compiled
+    reference; a shard from the middle (what another GPU of the job owns: shard.plan) gives the same bytes."""
+    import torch
+    w = msdr.workloads.get("c5", K)
+    C = w.channels
+    dev = torch.device("cuda:0")
+    g = msdr.ReceiveChain(C, max_taps=w.max_taps)
+    w.configure(g)
+    g.set_stream(torch.cuda.current_stream().cuda_stream)
+    chans = msdr.workloads.sample_channels(C, want=64)
+    o = _checker_for(msdr, _best_checker(orc), w, chans)
+    idx = torch.tensor(chans, device=dev)
+    sh = msdr.shard.plan(C, 8, rank=3)
+    g3 = msdr.ReceiveChain(sh.n, max_taps=w.max_taps)
+    w.configure(g3, sh.ch0)
+    g3.set_stream(torch.cuda.current_stream().cuda_stream)
+    for k in range(3):
+        x = msdr.synth.torch_batch(C, 8 * 128, dev, w.fs, n0=k * 1024)
+        y = torch.empty_like(x)
+        g.update_device(x.data_ptr(), y.data_ptr(), 8, x.stride(0))
+        xs = x[sh.ch0:sh.ch0 + sh.n].contiguous()
+        y3 = torch.empty_like(xs)
+        g3.update_device(xs.data_ptr(), y3.data_ptr(), 8, xs.stride(0))
+        torch.cuda.synchronize()
+        assert_same(y[idx].cpu().numpy(), o.run(np.ascontiguousarray(x[idx].cpu().numpy()))[0], f"C5 layout, update {k}")
+        assert torch.equal(y3, y[sh.ch0:sh.ch0 + sh.n]), f"shard of rank 3 of 8 differs in update {k}"
+    assert g.plan_build_count() == 1
+
+
+def test_list_setters_match_ranged_setters(msdr, K):
+    """msdr_chain_set_mode_list / msdr_fir_init_q15_list == the ranged calls channel by channel (same output bytes, same state)."""
+    import torch
+    C, nb = 300, 6
+    dev = torch.device("cuda:0")
+    w = msdr.workloads.get("c3", K)
+    x = msdr.synth.torch_batch(C, nb * 128, dev)
+    ga, _ = _setup(msdr, K, C)          # ranged / per-channel calls
+    gb = msdr.ReceiveChain(C)
+    w.configure(gb)                     # list calls
+    outs = []
+    for g in (ga, gb):
+        y = torch.empty_like(x)
+        g.set_stream(torch.cuda.current_stream().cuda_stream)
+        g.update_device(x.data_ptr(), y.data_ptr(), nb, x.stride(0))
+        torch.cuda.synchronize()
+        outs.append(y)
+    assert torch.equal(outs[0], outs[1])
+    for c in (0, 1, 2, 3, 299):
+        sa, sb = ga.get_state(c), gb.get_state(c)
+        assert sa.mode == sb.mode and sa.num_taps == sb.num_taps and list(sa.fir_history) == list(sb.fir_history)
+        assert [list(r) for r in sa.biquad_definition] == [list(r) for r in sb.biquad_definition]
+    # re-binding by list zeroes exactly the listed channels' delay lines (init_FIR, Minimal-SDR.ino:902-903)
+    gb.fir_init_list(*w.tables_for(ol.MODE_USB), [1, 5])
+    assert not any(gb.get_state(1).fir_history) and not any(gb.get_state(5).fir_history) and any(gb.get_state(2).fir_history)
+    with pytest.raises(msdr.MsdrError):
+        gb.fir_set_coefficients(np.zeros(10, np.int16), np.zeros(10, np.int16), 0, 1)  # wrong tap count: refused before the C ABI reads past the arrays
