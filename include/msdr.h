@@ -75,7 +75,8 @@ typedef struct {
  * and no FIR bound (the sketch always calls init_FIR() in setup(), Minimal-SDR.ino:404). */
 int msdr_chain_create(msdr_chain **out, int device, uint32_t n_channels, uint32_t max_taps, uint32_t flags);
 void msdr_chain_destroy(msdr_chain *chain);
-/* Runs the chain's work on a caller-provided cudaStream_t (e.g. torch's current stream); NULL = own stream. */
+/* Runs the chain's work on a caller-provided cudaStream_t (e.g. torch's current stream); NULL = the chain's own non-blocking
+ * stream, which is NOT ordered with the legacy default stream - pass cudaStreamLegacy ((cudaStream_t)1) to run there. */
 int msdr_chain_set_stream(msdr_chain *chain, void *cuda_stream);
 int msdr_chain_synchronize(msdr_chain *chain);
 const char *msdr_last_error(const msdr_chain *chain); /* chain may be NULL: error of the last failed create */

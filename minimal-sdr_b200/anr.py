@@ -48,7 +48,9 @@ class Anr:
         return self._ck(self._L.msdr_anr_update_device(self.h, int(mode), C.c_void_p(int(d_data)), int(n_blocks), int(stride)))
 
     def set_stream(self, cuda_stream):
-        return self._ck(self._L.msdr_anr_set_stream(self.h, C.c_void_p(int(cuda_stream))))
+        # 0 = torch's default stream -> cudaStreamLegacy (handle 1); None = the object's own stream (see ReceiveChain.set_stream)
+        h = 0 if cuda_stream is None else (int(cuda_stream) or 1)
+        return self._ck(self._L.msdr_anr_set_stream(self.h, C.c_void_p(h)))
 
     def synchronize(self):
         return self._ck(self._L.msdr_anr_synchronize(self.h))

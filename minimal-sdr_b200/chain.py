@@ -156,7 +156,10 @@ class ReceiveChain:
         return self._ck(self._L.msdr_chain_set_option(self.h, key.encode(), int(value)))
 
     def set_stream(self, cuda_stream_handle):
-        return self._ck(self._L.msdr_chain_set_stream(self.h, C.c_void_p(int(cuda_stream_handle) if cuda_stream_handle else 0)))
+        """cudaStream_t handle as an int.  0 is what torch reports for its default stream: it is passed on as cudaStreamLegacy
+        (handle 1), so the chain's kernels are ordered with work queued there; None = the chain's own non-blocking stream."""
+        h = 0 if cuda_stream_handle is None else (int(cuda_stream_handle) or 1)
+        return self._ck(self._L.msdr_chain_set_stream(self.h, C.c_void_p(h)))
 
     # -- the hot path ----------------------------------------------------------------------------
     def update(self, x, out=None):

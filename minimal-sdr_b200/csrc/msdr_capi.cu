@@ -103,7 +103,11 @@ struct msdr_chain {
     uint32_t *d_rowmap = nullptr, *d_grp = nullptr, *d_wave_rb0 = nullptr;
     uint4 *d_rb = nullptr;
     uint8_t *d_bmat = nullptr;
-  } plan;
+  };
+  // one plan per updated channel range: msdr_chain_update cuts wide chains into channel chunks, each its own range
+  static constexpr size_t kMaxPlans = 64;
+  std::vector<TcPlan> plans;
+  size_t plan_victim = 0;
   int *d_tile_cnt = nullptr;
   size_t tile_cnt_len = 0;
 
@@ -307,7 +311,7 @@ void msdr_chain_destroy(msdr_chain *chain)
   cudaSetDevice(chain->device);
   if (chain->stream) cudaStreamSynchronize(chain->stream);
   cudaFree(chain->d_mode); cudaFree(chain->d_set); cudaFree(chain->d_hist); cudaFree(chain->d_bq);
-  cudaFree(chain->plan.d_rowmap); cudaFree(chain->plan.d_grp); cudaFree(chain->plan.d_wave_rb0); cudaFree(chain->plan.d_rb); cudaFree(chain->plan.d_bmat);
+  for (auto &pl : chain->plans) { cudaFree(pl.d_rowmap); cudaFree(pl.d_grp); cudaFree(pl.d_wave_rb0); cudaFree(pl.d_rb); cudaFree(pl.d_bmat); }
   cudaFree(chain->d_tile_cnt); cudaFree(chain->d_pll);
   cudaFree(chain->d_anr_d); cudaFree(chain->d_anr_w); cudaFree(chain->d_anr_lidx); cudaFree(chain->d_anr_ngamma); cudaFree(chain->d_anr_idx);
   cudaFree(chain->pll.d_kind); cudaFree(chain->pll.d_anr_mode);
@@ -543,9 +547,8 @@ int msdr_biquad_set_coefficients(msdr_chain *chain, int object, uint32_t ch0, ui
 
 namespace {
 
-void free_tc_plan(msdr_chain *chain)
+void free_tc_plan(msdr_chain::TcPlan &pl)
 {
-  msdr_chain::TcPlan &pl = chain->plan;
   cudaFree(pl.d_rowmap); cudaFree(pl.d_grp); cudaFree(pl.d_wave_rb0); cudaFree(pl.d_rb); cudaFree(pl.d_bmat);
   pl = msdr_chain::TcPlan{};
 }
@@ -558,12 +561,21 @@ void free_tc_plan(msdr_chain *chain)
 // want_dual: the caller would like waves of 2 x sms chains (two chain sets per SM); the plan is built with that width only if the
 // window leaves room for the second set of chain slots (rings[3]), which is known before any row is sorted — so the wave width
 // is chosen once and an unchanged configuration always hits the cache (256 taps beyond 148 groups used to rebuild twice per update).
-int build_tc_plan(msdr_chain *chain, uint32_t ch0, uint32_t nch, uint32_t sms, bool want_dual)
+int build_tc_plan(msdr_chain *chain, uint32_t ch0, uint32_t nch, uint32_t sms, bool want_dual, const msdr_chain::TcPlan **out)
 {
-  msdr_chain::TcPlan &pl = chain->plan;
-  if (pl.version == chain->meta_version && pl.ch0 == ch0 && pl.nch == nch && pl.sms == sms && pl.want_dual == want_dual) return MSDR_OK;
-  CK(cudaStreamSynchronize(chain->stream)); // a launch in flight may still read the old plan
-  free_tc_plan(chain);
+  for (const auto &c : chain->plans)
+    if (c.version == chain->meta_version && c.ch0 == ch0 && c.nch == nch && c.sms == sms && c.want_dual == want_dual) { *out = &c; return MSDR_OK; }
+  CK(cudaStreamSynchronize(chain->stream)); // a launch in flight may still read the plan that is replaced
+  size_t slot = chain->plans.size();
+  for (size_t i = 0; i < chain->plans.size(); ++i)
+    if (chain->plans[i].version != chain->meta_version) { slot = i; break; } // stale: a table or a binding changed since
+  if (slot == chain->plans.size()) {
+    if (chain->plans.size() < msdr_chain::kMaxPlans) chain->plans.emplace_back();
+    else slot = chain->plan_victim++ % msdr_chain::kMaxPlans;
+  }
+  msdr_chain::TcPlan &pl = chain->plans[slot];
+  free_tc_plan(pl);
+  *out = &pl;
   chain->plan_builds++;
   pl.version = chain->meta_version; pl.ch0 = ch0; pl.nch = nch; pl.sms = sms; pl.want_dual = want_dual;
 
@@ -778,9 +790,10 @@ int msdr_chain_update_range_device(msdr_chain *chain, uint32_t ch0, uint32_t nch
     // more channel groups than SMs: two chain sets per SM (waves of 2 x SMs groups), unless a study variant asks for a
     // specific shape (bits 7, 8) or forbids it (bit 9)
     const bool want_dual = NG > (uint32_t)sms && !(chain->variant & (128 | 256 | 512 | 2048));
-    int st = build_tc_plan(chain, ch0, nch, (uint32_t)sms, want_dual);
+    const msdr_chain::TcPlan *plp = nullptr;
+    int st = build_tc_plan(chain, ch0, nch, (uint32_t)sms, want_dual, &plp);
     if (st != MSDR_OK) return st;
-    const msdr_chain::TcPlan &pl = chain->plan;
+    const msdr_chain::TcPlan &pl = *plp;
     const bool dual = pl.dual; // false when the second set of chain slots does not fit next to this window (256 taps)
     use_tc = pl.usable;
     if (use_tc) {
@@ -881,9 +894,15 @@ int msdr_chain_update(msdr_chain *chain, const int16_t *in, int16_t *out, uint32
   // chunk = (channel range) x (block range).  Whole channel set and ~64 MiB per direction when it fits, so each kernel
   // still sees thousands of channels; huge chains are cut along channels as well.
   uint32_t Cc = chain->host_chunk_channels;
-  if (Cc == 0) Cc = 1u << 19;
-  Cc = std::max<uint32_t>(kGroup, std::min(Cc, (chain->C + kGroup - 1) / kGroup * kGroup) / kGroup * kGroup);
   uint32_t nbk = chain->host_chunk_blocks;
+  if (Cc == 0) {
+    // wide chains: keep the chunks deep in time (a kernel over a handful of blocks is all start-up) and cut along the channels
+    // instead, ~128 MiB per direction and chunk; every distinct channel range has its own cached row plan (kMaxPlans)
+    const uint32_t deep = std::min<uint32_t>(n_blocks, nbk ? nbk : 64u);
+    const size_t want = ((size_t)128 << 20) / ((size_t)deep * MSDR_BLOCK_SAMPLES * 2);
+    Cc = (uint32_t)std::min<size_t>(1u << 19, std::max<size_t>(8192, (want + 4095) / 4096 * 4096));
+  }
+  Cc = std::max<uint32_t>(kGroup, std::min(Cc, (chain->C + kGroup - 1) / kGroup * kGroup) / kGroup * kGroup);
   if (nbk == 0) nbk = (uint32_t)std::max<size_t>(1, ((size_t)64 << 20) / ((size_t)std::min(Cc, chain->C) * MSDR_BLOCK_SAMPLES * 2));
   nbk = std::min(nbk, n_blocks);
   const size_t Lc = (size_t)nbk * MSDR_BLOCK_SAMPLES; // device row pitch of a chunk
