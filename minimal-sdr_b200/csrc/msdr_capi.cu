@@ -903,7 +903,7 @@ int msdr_chain_update(msdr_chain *chain, const int16_t *in, int16_t *out, uint32
     Cc = (uint32_t)std::min<size_t>(1u << 19, std::max<size_t>(8192, (want + 4095) / 4096 * 4096));
   }
   Cc = std::max<uint32_t>(kGroup, std::min(Cc, (chain->C + kGroup - 1) / kGroup * kGroup) / kGroup * kGroup);
-  if (nbk == 0) nbk = (uint32_t)std::max<size_t>(1, ((size_t)64 << 20) / ((size_t)std::min(Cc, chain->C) * MSDR_BLOCK_SAMPLES * 2));
+  if (nbk == 0) nbk = (uint32_t)std::max<size_t>(64, ((size_t)64 << 20) / ((size_t)std::min(Cc, chain->C) * MSDR_BLOCK_SAMPLES * 2));
   nbk = std::min(nbk, n_blocks);
   const size_t Lc = (size_t)nbk * MSDR_BLOCK_SAMPLES; // device row pitch of a chunk
   const size_t slot_samples = (size_t)Cc * Lc;
