@@ -100,6 +100,7 @@ struct msdr_chain {
     uint64_t version = 0;
     uint32_t ch0 = 0, nch = 0, sms = 0, W = 0, K = 0, rings[4] = {0, 0, 0, 0}, n_rb = 0, n_waves = 0;
     bool usable = false, want_dual = false, dual = false;
+    uint32_t ring_v5 = 0; // msdr_chain_v5.cu: operand ring depth, 0 = the window does not fit that kernel
     uint32_t *d_rowmap = nullptr, *d_grp = nullptr, *d_wave_rb0 = nullptr;
     uint4 *d_rb = nullptr;
     uint8_t *d_bmat = nullptr;
@@ -586,6 +587,7 @@ int build_tc_plan(msdr_chain *chain, uint32_t ch0, uint32_t nch, uint32_t sms, b
   CK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, chain->device));
   if (!chain_v4_config(K, smem_max, pl.rings)) { pl.usable = false; return MSDR_OK; }
   pl.K = K;
+  pl.ring_v5 = chain_v5_config(K, smem_max);
   pl.dual = want_dual && pl.rings[3] != 0;
   const uint32_t W = pl.W = sms * (pl.dual ? 2u : 1u);
 
@@ -790,8 +792,70 @@ int msdr_chain_update_range_device(msdr_chain *chain, uint32_t ch0, uint32_t nch
     // more channel groups than SMs: two chain sets per SM (waves of 2 x SMs groups), unless a study variant asks for a
     // specific shape (bits 7, 8) or forbids it (bit 9)
     const bool want_dual = NG > (uint32_t)sms && !(chain->variant & (128 | 256 | 512 | 2048));
+    // Many channels: the row-block kernel (msdr_chain_v5.cu), one CTA per 128 channels of one tap table walking through time.  It
+    // needs enough row blocks to fill the SMs (kV5MinChannels: below that the pinned chains of msdr_chain_v4.cu win);
+    // variant bit 12 forces it for any channel count (parity tests), bit 13 forbids it.
+    constexpr uint32_t kV5MinChannels = 12288;
+    bool use_v5 = ((chain->variant & 4096) || nch >= kV5MinChannels) && !(chain->variant & (8192 | 128 | 256 | 512 | 2048));
     const msdr_chain::TcPlan *plp = nullptr;
-    int st = build_tc_plan(chain, ch0, nch, (uint32_t)sms, want_dual, &plp);
+    int st = MSDR_OK;
+    if (use_v5) { // a plan with ONE wave: rows sorted by table over the whole range (wave width = all groups)
+      st = build_tc_plan(chain, ch0, nch, NG, false, &plp);
+      if (st != MSDR_OK) return st;
+      if (!plp->usable || !plp->ring_v5) use_v5 = false; // window too long (256 taps): the chain kernel below
+    }
+    if (use_v5) {
+      const msdr_chain::TcPlan &pl = *plp;
+      p.NG = NG;
+      p.n_items = pl.n_rb;
+      p.tc_rowmap = pl.d_rowmap; p.tc_rb = pl.d_rb; p.tc_grp = pl.d_grp; p.tc_wave_rb0 = pl.d_wave_rb0; p.tc_bmat = pl.d_bmat;
+      p.tc_K = pl.K; p.tc_ring = pl.ring_v5;
+      if (chain->timed) {
+        int stu = usage_resolve(chain);
+        if (stu != MSDR_OK) return stu;
+        CK(cudaEventRecord(chain->ev0, chain->stream));
+      }
+      {
+        int stl = syncam_lane_prepare(chain, ch0, nch, d_in, stride, p.L);
+        if (stl != MSDR_OK) return stl;
+      }
+      static const bool prof5 = getenv("MSDR_PROF") != nullptr;
+      long long *d_prof5 = nullptr;
+      if (prof5) {
+        CK(cudaMalloc(&d_prof5, (size_t)sms * 64 * sizeof(long long)));
+        CK(cudaMemsetAsync(d_prof5, 0, (size_t)sms * 64 * sizeof(long long), chain->stream));
+        p.prof = d_prof5;
+      }
+      CK(launch_chain_v5(p, chain->stream, chain->variant, sms, &chain->last_info));
+      chain->last_kernel = "msdr::v5::chain_kernel (fused mix + tensor-core FIR pair + demod + biquad cascade; one CTA per 128-channel row block)";
+      {
+        int stl = syncam_lane_finish(chain, ch0, d_out, stride, p.L);
+        if (stl != MSDR_OK) return stl;
+      }
+      if (chain->timed) {
+        CK(cudaEventRecord(chain->ev1, chain->stream));
+        chain->usage_pending = true;
+        chain->usage_blocks = n_blocks;
+      }
+      chain->launches++;
+      if (d_prof5) {
+        const uint32_t g = (uint32_t)chain->last_info.grid;
+        std::vector<long long> h((size_t)g * 64);
+        CK(cudaMemcpyAsync(h.data(), d_prof5, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, chain->stream));
+        CK(cudaStreamSynchronize(chain->stream));
+        cudaFree(d_prof5);
+        static const char *role[7] = {"convert", "mma", "epilogue", "biquad1", "biquad2", "load", "store"};
+        fprintf(stderr, "[msdr prof v5] grid %u, %u row blocks, mean cycles per CTA (counter 0..3):\n", g, pl.n_rb);
+        for (int r = 0; r < 7; ++r) {
+          double m[4] = {0, 0, 0, 0};
+          for (uint32_t b = 0; b < g; ++b)
+            for (int i = 0; i < 4; ++i) m[i] += (double)h[(size_t)b * 64 + r * 4 + i] / g;
+          fprintf(stderr, "  %-9s %10.0f %10.0f %10.0f %10.0f\n", role[r], m[0], m[1], m[2], m[3]);
+        }
+      }
+      return MSDR_OK;
+    }
+    st = build_tc_plan(chain, ch0, nch, (uint32_t)sms, want_dual, &plp);
     if (st != MSDR_OK) return st;
     const msdr_chain::TcPlan &pl = *plp;
     const bool dual = pl.dual; // false when the second set of chain slots does not fit next to this window (256 taps)

@@ -1,0 +1,469 @@
+// msdr_chain_v5.cu — K1c: the fused receive chain for MANY channels, one persistent CTA per SM that owns whole row blocks.
+//
+//   int16 IF samples -> [fs/4 mix folded into the byte planes] -> FIR pair as int8 Toeplitz GEMMs on tcgen05.mma (exact mod 2^32,
+//   msdr_fir_tc.cu) -> >>15, SSAT16 -> SSB sum / AM envelope -> biquad object 1 -> biquad object 2 -> int16 audio
+//
+// Reference semantics: Minimal-SDR.ino:546-558 (mix), arm_fir_fast_q15.c:60-329 (FIR), Minimal-SDR.ino:589-628 (demod),
+// filter_biquad.cpp:33-82 (biquad).
+//
+// msdr_chain_v4.cu is built around FEW channels: its biquad chains are pinned to SMs and fed through global memory by FIR producers
+// that run anywhere, because 4096 channels are only 128 warps of serial recurrence.  With tens of thousands of channels there is
+// enough recurrence for every SM, so here nothing is decoupled: a CTA takes a row block (128 channels that share one tap table,
+// msdr_capi.cu::build_tc_plan) and walks it through time, 64 samples per tile, every stage handing its tile to the next through
+// shared memory.  The FIR -> biquad intermediate never leaves the SM, no counters are polled, DRAM traffic is the algorithmic
+// 2 B in + 2 B out per sample.  23 warps, roles by warp id (warp id % 4 = SM sub-partition):
+//
+//   warp 21        load      cp.async (LDGSTS) of the tile's raw rows (128 rows x 128 B, gathered through the row map; history or
+//                            zeros in front of sample 0) into a 2-stage staging ring; completion arrives on an mbarrier
+//   warps 16-19    convert   thread = row: raw int16 -> fs/4 sign fold -> four byte planes in the ring of A operands (the window of a
+//                            tile is the last K/32 ring entries, so every sample is converted exactly once per launch)
+//   warp 20        MMA       one elected lane: 2 branches x 4 byte-plane products x K/32 MMAs (M128 N64 K32) per tile, tcgen05.commit
+//   warps 0-7      epilogue  TMEM lane quadrant = warp id % 4 (hardware rule), two warps per quadrant take 32 of the 64 columns each:
+//                            tcgen05.ld, recombine, >>15, SSAT16 -> packed (I, Q) in registers, hand TMEM back, demodulate, park the
+//                            int16 rows in one of four tile slots
+//   warps 8-11     biquad 1  lane = row: object 1 over the slot in place (state in registers for the whole row block)
+//   warps 12-15    biquad 2  object 2 likewise
+//   warp 22        store     slot -> `out`, 128 B per row and tile, coalesced
+//
+// Every sub-partition hosts two epilogue warps, one warp of each biquad object and one converter: the TMEM read port (64 B/clk per
+// SM, 24 B per output sample for the six int32 accumulators), the integer multiplier (5 IMAD.HI per sample and stage) and the issue
+// slots are all used evenly.
+#include "msdr_chain_common.cuh"
+#include "msdr_tc_common.cuh"
+
+namespace msdr {
+namespace v5 {
+
+using namespace tc;
+
+constexpr int kWarps = 23;
+constexpr int kThreads = kWarps * 32;
+constexpr int kEpiWarps = 8, kBqA0 = 8, kBqB0 = 12, kConv0 = 16, kMmaWarp = 20, kLoadWarp = 21, kStoreWarp = 22;
+constexpr int RS = 2;                  // raw staging stages
+constexpr int NS = 4;                  // tile slots: epilogue | biquad 1 | biquad 2 | store
+constexpr int YW = N / 2 + 4;          // slot row pitch in words (4 mod 32: conflict-free row-wise 128-bit accesses)
+constexpr uint32_t RAWP = 2 * N + 16;  // raw staging row pitch in bytes
+constexpr uint32_t kRawStageBytes = M * RAWP;
+constexpr uint32_t kSlotBytes = M * YW * 4;
+constexpr uint32_t kCtrlBytes = 2048;
+constexpr uint32_t kPad = 0xFFFFFFFFu;
+
+struct __align__(16) Ctrl {
+  uint64_t raw_full[RS];        // load -> convert    : the stage's copies have landed (32 arrivals, cp.async.mbarrier.arrive.noinc)
+  uint64_t raw_free[RS];        // convert -> load    : stage read (4 arrivals)
+  uint64_t a_full[RING_MAX];    // convert -> MMA     : pair converted (4 arrivals)
+  uint64_t blk_free[RING_MAX];  // MMA -> convert     : pair no longer read (tcgen05.commit)
+  uint64_t tmem_full;           // MMA -> epilogue    : accumulators complete (tcgen05.commit)
+  uint64_t tmem_empty;          // epilogue -> MMA    : accumulators drained (8 arrivals)
+  uint64_t b_full;              // convert -> MMA     : Toeplitz operand of the row block's table in place (4 arrivals)
+  uint64_t b_free;              // MMA -> convert     : all MMAs of the previous row block complete (tcgen05.commit)
+  uint64_t y_full[NS][4];       // epilogue -> biquad 1 (per 32-row quarter; 2 arrivals: both column halves)
+  uint64_t ab_full[NS][4];      // biquad 1 -> biquad 2 (per quarter)
+  uint64_t st_full[NS];         // biquad 2 -> store  (4 arrivals)
+  uint64_t slot_free[NS];       // store -> epilogue  (8 waiters)
+  uint32_t tmem_base;
+  uint32_t rowmap_ld[M];        // the loader's and the store warp's own copies of the row map
+  uint32_t rowmap_st[M];
+};
+static_assert(sizeof(Ctrl) <= kCtrlBytes, "Ctrl must fit its smem slot");
+
+size_t smem_bytes(uint32_t K, uint32_t ring)
+{
+  return (size_t)kCtrlBytes + 4u * a_plane_bytes(ring) + 4u * N * K + (size_t)RS * kRawStageBytes + (size_t)NS * kSlotBytes + 1024u;
+}
+
+// developer profile (MSDR_PROF=1): per-CTA cycle totals, slot = role * 4 + counter
+struct Prof {
+  long long *base;
+  long long acc[4];
+  long long t;
+  __device__ __forceinline__ Prof(long long *b, int role) : base(b ? b + (size_t)blockIdx.x * 64 + role * 4 : nullptr), acc{0, 0, 0, 0}, t(0) {}
+  __device__ __forceinline__ void start() { if (base) t = clock64(); }
+  __device__ __forceinline__ void lap(int i) { if (base) { const long long n = clock64(); acc[i] += n - t; t = n; } }
+  __device__ __forceinline__ void flush() { if (base && (threadIdx.x & 31) == 0) for (int i = 0; i < 4; ++i) base[i] = acc[i]; }
+};
+
+__device__ __forceinline__ uint4 lds128(uint32_t a)
+{
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, const uint4 &v)
+{
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// 64 samples of one row in place: eight 128-bit words, two register sets alternating (the next eight samples are on their way
+// while the recurrence runs)
+template <class BQ>
+__device__ __forceinline__ void bq_tile(BQ (&st)[1], uint32_t a)
+{
+  uint4 v0 = lds128(a), v1;
+#pragma unroll 1
+  for (int q = 0; q < N / 8; q += 2) {
+    v1 = lds128(a + 16u * (uint32_t)(q + 1));
+    v0.x = bq_word<1>(st, v0.x);
+    v0.y = bq_word<1>(st, v0.y);
+    v0.z = bq_word<1>(st, v0.z);
+    v0.w = bq_word<1>(st, v0.w);
+    sts128(a + 16u * (uint32_t)q, v0);
+    if (q + 2 < N / 8) v0 = lds128(a + 16u * (uint32_t)(q + 2));
+    v1.x = bq_word<1>(st, v1.x);
+    v1.y = bq_word<1>(st, v1.y);
+    v1.z = bq_word<1>(st, v1.z);
+    v1.w = bq_word<1>(st, v1.w);
+    sts128(a + 16u * (uint32_t)(q + 1), v1);
+  }
+}
+
+// one branch of eight output columns: the three byte-plane accumulators -> the reference's accumulator mod 2^32
+__device__ __forceinline__ void drain8(uint32_t taddr, uint32_t (&acc)[8])
+{
+  uint32_t a0[8], a1[8], a2[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(a0[0]), "=r"(a0[1]), "=r"(a0[2]), "=r"(a0[3]), "=r"(a0[4]), "=r"(a0[5]), "=r"(a0[6]), "=r"(a0[7]) : "r"(taddr));
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(a1[0]), "=r"(a1[1]), "=r"(a1[2]), "=r"(a1[3]), "=r"(a1[4]), "=r"(a1[5]), "=r"(a1[6]), "=r"(a1[7]) : "r"(taddr + (uint32_t)N));
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(a2[0]), "=r"(a2[1]), "=r"(a2[2]), "=r"(a2[3]), "=r"(a2[4]), "=r"(a2[5]), "=r"(a2[6]), "=r"(a2[7]) : "r"(taddr + 2u * (uint32_t)N));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = (a0[j] << 16) + (a1[j] << 8) + a2[j]; // mod 2^32, like the reference accumulator
+}
+
+// demodulation switch (Minimal-SDR.ino:589-628) over the 32 packed (I | Q << 16) words a thread holds -> 16 words of int16 pairs
+template <int KIND>
+__device__ __forceinline__ void demod_regs(const uint32_t (&iq)[32], int sgn, uint32_t (&out)[16])
+{
+#pragma unroll
+  for (int c0 = 0; c0 < 32; c0 += 8) { // eight samples in flight: the envelope kinds are a dependent-latency problem
+    int y[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) y[j] = demod_inline<KIND>((int)(short)(iq[c0 + j] & 0xFFFFu), (int)iq[c0 + j] >> 16, sgn);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[c0 / 2 + j] = ((uint32_t)y[2 * j] & 0xFFFFu) | ((uint32_t)y[2 * j + 1] << 16);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
+{
+  using BQ = BqStage;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023u) & ~(uintptr_t)1023u);
+  const uint32_t K = p.tc_K, KS = K / 32, ring = p.tc_ring;
+  const uint32_t a_plane = a_plane_bytes(ring), b_plane = N * K;
+  Ctrl *pc = reinterpret_cast<Ctrl *>(smem);
+  uint8_t *sA = smem + kCtrlBytes;
+  uint8_t *sB = sA + 4 * a_plane;
+  unsigned char *sRaw = sB + 4 * b_plane;
+  unsigned char *sY = sRaw + RS * kRawStageBytes;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < RS; ++i) { mbar_init(&pc->raw_full[i], 32); mbar_init(&pc->raw_free[i], 4); }
+    for (int i = 0; i < RING_MAX; ++i) { mbar_init(&pc->a_full[i], 4); mbar_init(&pc->blk_free[i], 1); }
+    mbar_init(&pc->tmem_full, 1);
+    mbar_init(&pc->tmem_empty, kEpiWarps);
+    mbar_init(&pc->b_full, 4);
+    mbar_init(&pc->b_free, 1);
+    for (int s = 0; s < NS; ++s) {
+      for (int q = 0; q < 4; ++q) { mbar_init(&pc->y_full[s][q], 2); mbar_init(&pc->ab_full[s][q], 1); }
+      mbar_init(&pc->st_full[s], 4);
+      mbar_init(&pc->slot_free[s], 1);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc_512(&pc->tmem_base);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = pc->tmem_base;
+
+  const uint32_t NT = p.L / N;              // tiles per row block (L is a multiple of 128)
+  const uint32_t npairs = NT + KS - 1;      // ring entries per row block: KS - 1 of history in front
+  const uint32_t n_rb = p.n_items;
+  const int Hs = (int)p.H;
+
+  if (warp == kLoadWarp) {
+    // ================================================================== raw rows: global -> staging ring
+    Prof prof(p.prof, 5);
+    uint32_t pseq = 0;
+    const int r0 = lane >> 3, c = lane & 7;
+    for (uint32_t rb = blockIdx.x; rb < n_rb; rb += gridDim.x) {
+      const uint32_t *rmap = p.tc_rowmap + (size_t)rb * M;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) pc->rowmap_ld[lane + 32 * i] = __ldg(rmap + lane + 32 * i);
+      __syncwarp();
+      for (int j = -(int)(KS - 1); j < (int)NT; ++j, ++pseq) {
+        const uint32_t stage = pseq % RS;
+        prof.start();
+        mbar_wait(&pc->raw_free[stage], ((pseq / RS) & 1u) ^ 1u);
+        prof.lap(0);
+        const long long s = (long long)j * N + 8 * c; // first sample of this lane's 16-byte chunk (negative: history)
+        const uint32_t dst0 = smem_u32(sRaw + stage * kRawStageBytes) + (uint32_t)r0 * RAWP + (uint32_t)c * 16u;
+        if (!(p.ablate & 1u)) {
+#pragma unroll 8
+          for (int i = 0; i < M / 4; ++i) {
+            const uint32_t row = pc->rowmap_ld[r0 + 4 * i];
+            const bool valid = row != kPad && s >= -(long long)Hs;
+            const int16_t *src = p.in; // never dereferenced when the copy size is 0 (zero fill)
+            if (valid) src = s >= 0 ? p.in + (size_t)row * p.stride + s : p.hist + ((size_t)p.ch0 + row) * p.H + (Hs + s);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + (uint32_t)i * 4u * RAWP), "l"(src), "r"(valid ? 16 : 0) : "memory");
+          }
+        }
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared.b64 [%0];" ::"r"(smem_u32(&pc->raw_full[stage])) : "memory");
+        prof.lap(1);
+      }
+      // carry the last H raw samples of every row: hist <- tail of (hist || in[0..L)).  This row block's reads of the old history
+      // were its first copies; they have landed once all of this lane's copies have.
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      __syncwarp();
+      const uint32_t hq = p.H >> 3; // uint4 per history row (<= 33)
+      for (int r = 0; r < M; ++r) {
+        const uint32_t row = pc->rowmap_ld[r];
+        if (row == kPad) continue;
+        uint4 *hrow = reinterpret_cast<uint4 *>(p.hist + ((size_t)p.ch0 + row) * p.H);
+        const uint4 *irow = reinterpret_cast<const uint4 *>(p.in + (size_t)row * p.stride);
+        uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
+        const uint32_t i0 = (uint32_t)lane, i1 = (uint32_t)lane + 32u;
+        if (p.L >= p.H) {
+          const uint4 *src = irow + ((p.L - p.H) >> 3);
+          if (i0 < hq) v0 = src[i0];
+          if (i1 < hq) v1 = src[i1];
+        } else {
+          const uint32_t lq = p.L >> 3, keep = hq - lq; // keep = old entries that survive
+          if (i0 < hq) v0 = (i0 < keep) ? __ldcg(hrow + i0 + lq) : irow[i0 - keep];
+          if (i1 < hq) v1 = (i1 < keep) ? __ldcg(hrow + i1 + lq) : irow[i1 - keep];
+        }
+        __syncwarp();
+        if (i0 < hq) hrow[i0] = v0;
+        if (i1 < hq) hrow[i1] = v1;
+      }
+      prof.lap(2);
+    }
+    prof.flush();
+  } else if (warp >= kConv0 && warp < kConv0 + 4) {
+    // ================================================================== byte planes: staging ring -> ring of A operands
+    Prof prof(p.prof, 0);
+    const uint32_t r = (uint32_t)(tid - kConv0 * 32); // row
+    uint32_t pseq = 0, nblk = 0;
+    for (uint32_t rb = blockIdx.x; rb < n_rb; rb += gridDim.x, ++nblk) {
+      { // Toeplitz operand of this row block's table; the previous row block's MMAs must be done with the old one
+        const uint32_t set = __ldg(&p.tc_rb[rb].x);
+        mbar_wait(&pc->b_free, (nblk & 1u) ^ 1u);
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.tc_bmat + (size_t)set * 4 * b_plane);
+        uint4 *dst = reinterpret_cast<uint4 *>(sB);
+        for (uint32_t i = r; i < 4 * b_plane / 16; i += M) dst[i] = __ldg(src + i);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&pc->b_full);
+      }
+      for (uint32_t u = 0; u < npairs; ++u, ++pseq) {
+        const uint32_t stage = pseq % RS, pos = pseq % ring;
+        prof.start();
+        mbar_wait(&pc->raw_full[stage], (pseq / RS) & 1u);
+        prof.lap(0);
+        mbar_wait(&pc->blk_free[pos], ((pseq / ring) & 1u) ^ 1u);
+        prof.lap(1);
+        if (!(p.ablate & 1u)) {
+          const uint32_t a = smem_u32(sRaw + stage * kRawStageBytes) + r * RAWP;
+          uint4 v0[4], v1[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { v0[j] = lds128(a + 16u * j); v1[j] = lds128(a + 64u + 16u * j); }
+          convert_store(sA, a_plane, pos, 0, r, v0);
+          convert_store(sA, a_plane, pos, 1, r, v1);
+        }
+        fence_proxy_async_smem(); // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(&pc->a_full[pos]); mbar_arrive(&pc->raw_free[stage]); }
+        prof.lap(2);
+      }
+    }
+    prof.flush();
+  } else if (warp == kMmaWarp) {
+    // ================================================================== tensor core
+    Prof prof(p.prof, 1);
+    IssueCtx ictx;
+    issue_init(ictx, sA, a_plane, sB, b_plane);
+    uint32_t qbase = 0, tseq = 0, nblk = 0;
+    for (uint32_t rb = blockIdx.x; rb < n_rb; rb += gridDim.x, ++nblk) {
+      mbar_wait(&pc->b_full, nblk & 1u);
+      for (uint32_t t = 0; t < NT; ++t, ++tseq) {
+        const uint32_t qt = qbase + t + KS - 1; // newest pair of this tile's window
+        prof.start();
+        mbar_wait(&pc->a_full[qt % ring], (qt / ring) & 1u);
+        prof.lap(0);
+        mbar_wait(&pc->tmem_empty, (tseq & 1u) ^ 1u);
+        prof.lap(1);
+        tc_fence_after();
+        if (!(p.ablate & 1u)) issue_tile(ictx, tmem, qt, KS, ring);
+        umma_commit(&pc->tmem_full);
+        umma_commit(&pc->blk_free[(qt - (KS - 1)) % ring]); // the oldest pair of the window is not read again
+        prof.lap(2);
+      }
+      for (uint32_t s = 1; s < KS; ++s) umma_commit(&pc->blk_free[(qbase + npairs - KS + s) % ring]);
+      umma_commit(&pc->b_free);
+      qbase += npairs;
+    }
+    __syncwarp();
+    prof.flush();
+  } else if (warp < kEpiWarps) {
+    // ================================================================== epilogue: TMEM -> demodulated int16 rows in a tile slot
+    Prof prof(p.prof, 2);
+    const int qd = warp & 3, half = warp >> 2;
+    const uint32_t trow = (uint32_t)(qd * 32 + lane);
+    const uint32_t lane_addr = tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)(half * 32);
+    uint32_t tseq = 0;
+    for (uint32_t rb = blockIdx.x; rb < n_rb; rb += gridDim.x) {
+      const uint32_t row = __ldg(p.tc_rowmap + (size_t)rb * M + trow);
+      const int kind = row != kPad ? demod_kind_of((int)p.mode[p.ch0 + row], p.am_q31) : 0;
+      for (uint32_t t = 0; t < NT; ++t, ++tseq) {
+        const uint32_t slot = tseq % NS;
+        uint32_t iq[32];
+        prof.start();
+        mbar_wait(&pc->tmem_full, tseq & 1u);
+        prof.lap(0);
+        tc_fence_after();
+        if (!(p.ablate & 1u)) {
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            uint32_t ai[8], aq[8];
+            drain8(lane_addr + (uint32_t)(8 * b), ai);
+            drain8(lane_addr + (uint32_t)(kAccPerBranch * N + 8 * b), aq);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) iq[8 * b + j] = pack_sat_iq((int)ai[j] >> 15, (int)aq[j] >> 15);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) iq[j] = 0u;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&pc->tmem_empty); // the next tile's MMAs overlap the demodulation
+        prof.lap(1);
+        uint32_t out[16];
+        if (kind <= 1) demod_regs<0>(iq, kind ? 1 : -1, out);
+        else if (kind == 2) demod_regs<2>(iq, 0, out);
+        else demod_regs<3>(iq, 0, out);
+        mbar_wait(&pc->slot_free[slot], ((tseq / NS) & 1u) ^ 1u);
+        prof.lap(2);
+        const uint32_t ya = smem_u32(sY + slot * kSlotBytes) + trow * (uint32_t)(YW * 4) + (uint32_t)(half * 64);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sts128(ya + 16u * j, make_uint4(out[4 * j], out[4 * j + 1], out[4 * j + 2], out[4 * j + 3]));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&pc->y_full[slot][qd]);
+        prof.lap(3);
+      }
+    }
+    prof.flush();
+    named_bar_sync(2, kEpiWarps * 32); // every epilogue warp has read its last accumulators
+    if (warp == 0) {
+      tc_fence_before();
+      tmem_dealloc_512(tmem);
+    }
+  } else if (warp >= kBqA0 && warp < kBqB0 + 4) {
+    // ================================================================== biquad objects: lane = row, state in registers
+    const bool isA = warp < kBqB0;
+    const int obj = isA ? 0 : 1, q = isA ? warp - kBqA0 : warp - kBqB0;
+    Prof prof(q == 0 ? p.prof : nullptr, isA ? 3 : 4);
+    const uint32_t trow = (uint32_t)(q * 32 + lane);
+    uint32_t tseq = 0;
+    for (uint32_t rb = blockIdx.x; rb < n_rb; rb += gridDim.x) {
+      const uint32_t row = __ldg(p.tc_rowmap + (size_t)rb * M + trow);
+      const bool active = row != kPad;
+      const uint32_t ch = p.ch0 + (active ? row : 0u);
+      // cascade structure of this lane's object: stages run while bit31 of word 7 says another follows (filter_biquad.cpp:75,79)
+      int nst = 1;
+      BQ st[1];
+      uint32_t fl = 0u;
+      if (active) {
+        for (int k = 0; k < 3 && (nst == k + 1); ++k)
+          if ((uint32_t)__ldcg(p.bq + (size_t)((obj * 4 + k) * 8 + 7) * p.Cpad + ch) & 0x80000000u) nst = k + 2;
+      }
+      const bool fast = __all_sync(0xffffffffu, nst == 1);
+      if (fast && active) bq_load_stage(st[0], fl, p.bq, p.Cpad, obj, 0, ch);
+      for (uint32_t t = 0; t < NT; ++t, ++tseq) {
+        const uint32_t slot = tseq % NS, phs = (tseq / NS) & 1u;
+        prof.start();
+        mbar_wait(isA ? &pc->y_full[slot][q] : &pc->ab_full[slot][q], phs);
+        prof.lap(0);
+        const uint32_t ya = smem_u32(sY + slot * kSlotBytes) + trow * (uint32_t)(YW * 4);
+        if (!(p.ablate & 2u) && active) {
+          if (fast) bq_tile(st, ya);
+          else { // generic cascade: stage-major over the tile like the reference (filter_biquad.cpp:44-79); state in global
+            for (int j = 0; j < nst; ++j) {
+              BQ gs[1];
+              uint32_t gf;
+              bq_load_stage(gs[0], gf, p.bq, p.Cpad, obj, j, ch);
+              bq_tile(gs, ya);
+              bq_store_stage(gs[0], gf, p.bq, p.Cpad, obj, j, ch);
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(isA ? &pc->ab_full[slot][q] : &pc->st_full[slot]);
+        prof.lap(1);
+      }
+      if (fast && active) bq_store_stage(st[0], fl, p.bq, p.Cpad, obj, 0, ch);
+    }
+    prof.flush();
+  } else if (warp == kStoreWarp) {
+    // ================================================================== final audio: slot -> `out`
+    Prof prof(p.prof, 6);
+    const int r0 = lane >> 3, c = lane & 7;
+    uint32_t tseq = 0;
+    for (uint32_t rb = blockIdx.x; rb < n_rb; rb += gridDim.x) {
+      const uint32_t *rmap = p.tc_rowmap + (size_t)rb * M;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) pc->rowmap_st[lane + 32 * i] = __ldg(rmap + lane + 32 * i);
+      __syncwarp();
+      for (uint32_t t = 0; t < NT; ++t, ++tseq) {
+        const uint32_t slot = tseq % NS, phs = (tseq / NS) & 1u;
+        prof.start();
+        mbar_wait(&pc->st_full[slot], phs);
+        prof.lap(0);
+        const uint32_t sa = smem_u32(sY + slot * kSlotBytes) + (uint32_t)r0 * (uint32_t)(YW * 4) + (uint32_t)c * 16u;
+        int16_t *gcol = p.out + (size_t)t * N + (size_t)c * 8;
+#pragma unroll 8
+        for (int i = 0; i < M / 4; ++i) {
+          const uint32_t row = pc->rowmap_st[r0 + 4 * i];
+          const uint4 v = lds128(sa + (uint32_t)i * 4u * (uint32_t)(YW * 4));
+          if (row != kPad) *reinterpret_cast<uint4 *>(gcol + (size_t)row * p.stride) = v;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&pc->slot_free[slot]);
+        prof.lap(1);
+      }
+    }
+    prof.flush();
+  }
+}
+
+} // namespace v5
+
+// deepest operand ring (at least one pair ahead of the window) that fits next to the staging ring and the tile slots; 0 = this
+// window is too long for the row-block kernel (256 taps: the chain kernel of msdr_chain_v4.cu takes it)
+uint32_t chain_v5_config(uint32_t K, int smem_max)
+{
+  if (K % 32u || K / 32u < 2u) return 0;
+  for (uint32_t ring = tc::RING_MAX; ring >= K / 32u + 1u; --ring)
+    if (v5::smem_bytes(K, ring) <= (size_t)smem_max) return ring;
+  return 0;
+}
+
+cudaError_t launch_chain_v5(const ChainParams &p_in, cudaStream_t stream, int variant, int sms, ChainLaunchInfo *info)
+{
+  using namespace v5;
+  ChainParams p = p_in;
+  p.ablate = ((uint32_t)variant >> 4) & 3u;
+  const size_t smem = smem_bytes(p.tc_K, p.tc_ring);
+  cudaError_t e = cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const uint32_t grid = p.n_items < (uint32_t)sms ? p.n_items : (uint32_t)sms;
+  if (info) { info->grid = (int)grid; info->block = kThreads; info->smem = smem; info->tile = tc::N; }
+  chain_kernel<<<grid, kThreads, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+} // namespace msdr

@@ -300,7 +300,7 @@ def test_update_range_device(msdr, orc, K):
 
 @pytest.mark.parametrize("variant,name", [(0, "default (tensor-core FIR, feed-forward helper warps)"), (2048, "tensor-core FIR + post warps"),
                                             (256, "tensor-core FIR, inline epilogue"), (128, "helper warps, forced"), (64, "CUDA-core FIR (v3)"),
-                                            (65, "v3, FP64 biquad")])
+                                            (65, "v3, FP64 biquad"), (4096, "row-block kernel (msdr_chain_v5.cu), forced")])
 def test_every_kernel_shape_is_bit_exact(msdr, orc, K, variant, name):
     """All shapes of the fused kernel (option "variant") produce the oracle's bits: mixed modes, ragged updates, 4-stage cascades on
     some channels, full-range (wrapping) taps on others, extreme inputs, a partial last group."""
@@ -402,3 +402,16 @@ def test_anr_channels_in_a_chain(msdr, orc, K):
     assert_same(yg[exact], yo[exact], "chain with ANR channels")
     a, b = yg[9].astype(np.float64), yo[9].astype(np.float64)        # SYNCAM + notch: float tolerance
     assert np.abs(a - b).max() <= 3 and np.sqrt(np.mean((a - b) ** 2)) <= 1e-4 * np.sqrt(np.mean(b ** 2)) + 0.05
+
+
+def test_whole_file_on_the_row_block_kernel():
+    """The row-block kernel (msdr_chain_v5.cu) is chosen for many channels; MSDR_VARIANT=4096 forces it for ANY channel count, and
+    this file's chain tests run again on it in a child process: single channels, ragged updates, partial row blocks, wrap / saturation
+    taps, multi-stage cascades, coefficient rewrites, state migration, host chunking, range updates, SYNCAM / ANR side lanes.
+    (256 taps do not fit that kernel: those cases fall back to the chain kernel, as in production.)"""
+    import subprocess
+    import sys
+    env = dict(os.environ, MSDR_VARIANT="4096")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-k",
+                        "not every_kernel_shape and not whole_file and not errors_match"], env=env, capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]

@@ -269,3 +269,40 @@ def test_list_setters_match_ranged_setters(msdr, K):
     assert not any(gb.get_state(1).fir_history) and not any(gb.get_state(5).fir_history) and any(gb.get_state(2).fir_history)
     with pytest.raises(msdr.MsdrError):
         gb.fir_set_coefficients(np.zeros(10, np.int16), np.zeros(10, np.int16), 0, 1)  # wrong tap count: refused before the C ABI reads past the arrays
+
+
+def test_row_block_kernel_equals_chain_kernel_at_size(msdr, orc, K):
+    """65 536 channels (512 row blocks on 148 SMs: several per CTA, table changes in between), three updates with state carried:
+    the row-block kernel (msdr_chain_v5.cu, the default at this size) and the chain kernel (msdr_chain_v4.cu, variant 8192 forbids
+    the former) produce the same bytes for EVERY channel, and sampled channels match the compiled reference."""
+    import torch
+    w = msdr.workloads.get("c5", K)
+    C = 65536
+    dev = torch.device("cuda:0")
+    chains = []
+    for variant in (0, 8192):
+        g = msdr.ReceiveChain(C, max_taps=w.max_taps)
+        g.set_option("variant", variant)
+        w.configure(g)
+        g.set_stream(torch.cuda.current_stream().cuda_stream)
+        chains.append(g)
+    chans = msdr.workloads.sample_channels(C)
+    o = _checker_for(msdr, _best_checker(orc), w, chans)
+    idx = torch.tensor(chans, device=dev)
+    n0 = 0
+    for nb in (16, 1, 7):
+        x = msdr.synth.torch_batch(C, nb * 128, dev, w.fs, n0=n0)
+        x[3] = -32768
+        ys = []
+        for g in chains:
+            y = torch.empty_like(x)
+            g.update_device(x.data_ptr(), y.data_ptr(), nb, x.stride(0))
+            ys.append(y)
+        torch.cuda.synchronize()
+        assert "v5" in chains[0].last_kernel() and "v4" in chains[1].last_kernel()
+        assert torch.equal(ys[0], ys[1]), f"row-block kernel != chain kernel, update of {nb} blocks"
+        assert_same(ys[0][idx].cpu().numpy(), o.run(np.ascontiguousarray(x[idx].cpu().numpy()))[0], f"65536 channels, update of {nb} blocks")
+        n0 += nb * 128
+    for c in (0, 1, 2, 3, 65535):  # carried state words are the same too
+        sa, sb = chains[0].get_state(c), chains[1].get_state(c)
+        assert list(sa.fir_history) == list(sb.fir_history) and [list(r) for r in sa.biquad_definition] == [list(r) for r in sb.biquad_definition]

@@ -1,0 +1,13 @@
+#!/bin/bash
+# first light of the row-block kernel: forced on small cases, then at size, then the throughput at 65536 / 131072 channels with role counters
+mkdir -p gpurun_out/r2
+O=gpurun_out/r2
+echo "== diag state (stream fix)"; timeout 300 python tools/diag/state_after_long_update.py 2>&1 | tail -8
+echo "== v5 forced, small"; timeout 600 python -m pytest tests/test_gpu_chain.py -x -q -m gpu -k "every_kernel_shape" 2>&1 | tail -8
+echo "== v5 whole file"; timeout 900 python -m pytest tests/test_gpu_chain.py -x -q -m gpu -k "whole_file" 2>&1 | tail -12
+echo "== at size"; timeout 900 python -m pytest tests/test_gpu_large.py -x -q -m gpu 2>&1 | tail -12
+for ch in 65536 131072; do
+  echo "== bench c5 $ch ch"; timeout 600 python bench.py --config c5 --channels $ch --steps 5 --no-cpu --e2e-steps 0 > $O/v5a_c5_$ch.json 2> $O/v5a_c5_$ch.err; cut -c1-220 $O/v5a_c5_$ch.json; tail -3 $O/v5a_c5_$ch.err
+done
+echo "== prof 131072"; MSDR_PROF=1 timeout 600 python bench.py --config c5 --channels 131072 --steps 1 --warmup 3 --no-cpu --no-parity --e2e-steps 0 2>&1 >/dev/null | tail -9 | tee $O/v5a_prof.txt
+for v in 16 32 48; do echo "== ablate $v"; timeout 600 python bench.py --config c5 --channels 131072 --steps 5 --no-cpu --no-parity --e2e-steps 0 --variant $v 2>/dev/null | cut -c1-160; done
