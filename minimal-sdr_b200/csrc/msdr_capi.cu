@@ -797,6 +797,14 @@ int msdr_chain_update_range_device(msdr_chain *chain, uint32_t ch0, uint32_t nch
     // variant bit 12 forces it for any channel count (parity tests), bit 13 forbids it.
     constexpr uint32_t kV5MinChannels = 12288;
     bool use_v5 = ((chain->variant & 4096) || nch >= kV5MinChannels) && !(chain->variant & (8192 | 128 | 256 | 512 | 2048));
+    if (use_v5) { // does the longest live table's window fit that kernel at all?  (known without sorting a single row: 256 taps do not)
+      int smem_max = 0;
+      CK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, chain->device));
+      uint32_t kp_live = 0;
+      for (const FirSet &fs : chain->sets)
+        if (fs.users) kp_live = std::max(kp_live, kp_of_taps(fs.T));
+      if (!chain_v5_config(tc_window_words_kp(kp_live), smem_max)) use_v5 = false;
+    }
     const msdr_chain::TcPlan *plp = nullptr;
     int st = MSDR_OK;
     if (use_v5) { // a plan with ONE wave: rows sorted by table over the whole range (wave width = all groups)

@@ -469,7 +469,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
           const int slot = (int)(pos % NSLOT_FF);
           const uint32_t phs = (pos / NSLOT_FF) & 1u;
           prof.start();
-          mbar_wait(isA ? &pc->ld_full[slot] : &pc->m_full[slot], phs);
+          mbar_wait(isA ? &pc->ld_full[slot] : &pc->m_full[slot], phs, 20);
           prof.lap(0);
           uint32_t *er = slotE(slot), *yr = slotY(slot);
           if (!(p.ablate & 2u) && active) {
@@ -524,7 +524,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
           uint4 v[SUB_FF / 8];
           prof.start();
           if (isLoad) {
-            mbar_wait(&pc->raw_full[slot], phs); // every lane's copies of this sub-tile have landed (raw loader, warp 8)
+            mbar_wait(&pc->raw_full[slot], phs, 32); // every lane's copies of this sub-tile have landed (raw loader, warp 8)
             prof.lap(0);
             prof.lap(1);
             const uint32_t *yr = slotY(slot);
@@ -533,7 +533,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
               for (int j = 0; j < SUB_FF / 8; ++j) v[j] = *reinterpret_cast<const uint4 *>(yr + 4 * j);
             }
           } else {
-            mbar_wait(&pc->ab_full[slot], phs);
+            mbar_wait(&pc->ab_full[slot], phs, 32);
             prof.lap(0);
             const uint32_t *yr = slotY(slot);
             if (active) {
@@ -709,7 +709,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
         const int slot = sbase + (int)(pos % NSLOT);
         const uint32_t phs = (pos / NSLOT) & 1u;
         prof.start();
-        mbar_wait(isA ? &pc->ld_full[slot] : &pc->ab_full[slot], phs);
+        mbar_wait(isA ? &pc->ld_full[slot] : &pc->ab_full[slot], phs, 20);
         prof.lap(0);
         const int nq = (int)(min((uint32_t)SUB, p.L - (uint32_t)k * SUB) >> 3);
         uint4 *r0 = reinterpret_cast<uint4 *>(reinterpret_cast<uint32_t *>(bq_base + (uint32_t)slot * kSlotBytes) + (uint32_t)lane * BW);

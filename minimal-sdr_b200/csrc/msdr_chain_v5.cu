@@ -45,7 +45,7 @@ constexpr int YW = N / 2 + 4;          // slot row pitch in words (4 mod 32: con
 constexpr uint32_t RAWP = 2 * N + 16;  // raw staging row pitch in bytes
 constexpr uint32_t kRawStageBytes = M * RAWP;
 constexpr uint32_t kSlotBytes = M * YW * 4;
-constexpr uint32_t kCtrlBytes = 2048;
+constexpr uint32_t kCtrlBytes = 1024;
 constexpr uint32_t kPad = 0xFFFFFFFFu;
 
 struct __align__(16) Ctrl {
@@ -53,8 +53,8 @@ struct __align__(16) Ctrl {
   uint64_t raw_free[RS];        // convert -> load    : stage read (4 arrivals)
   uint64_t a_full[RING_MAX];    // convert -> MMA     : pair converted (4 arrivals)
   uint64_t blk_free[RING_MAX];  // MMA -> convert     : pair no longer read (tcgen05.commit)
-  uint64_t tmem_full;           // MMA -> epilogue    : accumulators complete (tcgen05.commit)
-  uint64_t tmem_empty;          // epilogue -> MMA    : accumulators drained (8 arrivals)
+  uint64_t tmem_full[2];        // MMA -> epilogue    : accumulators of branch I / Q complete (tcgen05.commit)
+  uint64_t tmem_empty[2];       // epilogue -> MMA    : accumulators of branch I / Q drained (8 arrivals)
   uint64_t b_full;              // convert -> MMA     : Toeplitz operand of the row block's table in place (4 arrivals)
   uint64_t b_free;              // MMA -> convert     : all MMAs of the previous row block complete (tcgen05.commit)
   uint64_t y_full[NS][4];       // epilogue -> biquad 1 (per 32-row quarter; 2 arrivals: both column halves)
@@ -62,8 +62,6 @@ struct __align__(16) Ctrl {
   uint64_t st_full[NS];         // biquad 2 -> store  (4 arrivals)
   uint64_t slot_free[NS];       // store -> epilogue  (8 waiters)
   uint32_t tmem_base;
-  uint32_t rowmap_ld[M];        // the loader's and the store warp's own copies of the row map
-  uint32_t rowmap_st[M];
 };
 static_assert(sizeof(Ctrl) <= kCtrlBytes, "Ctrl must fit its smem slot");
 
@@ -133,6 +131,18 @@ __device__ __forceinline__ void drain8(uint32_t taddr, uint32_t (&acc)[8])
 }
 
 // demodulation switch (Minimal-SDR.ino:589-628) over the 32 packed (I | Q << 16) words a thread holds -> 16 words of int16 pairs
+// SSB kinds straight on the packed words p = I | Q << 16 (Minimal-SDR.ino:591-604: the int16 sum wraps, no saturation):
+//   USB  I + Q = upper half of p * 65537;   LSB  I - Q = I + ~Q + 1 = upper half of (p ^ 0xFFFF0000) * 65537 + 0x10000
+// one LOP3 and one IMAD per sample, one PRMT per pair.  xm / xc: the per-row XOR mask and addend (0 / 0 for USB).
+__device__ __forceinline__ void demod_ssb_regs(const uint32_t (&iq)[32], uint32_t xm, uint32_t xc, uint32_t (&out)[16])
+{
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const uint32_t t0 = (iq[2 * j] ^ xm) * 65537u + xc, t1 = (iq[2 * j + 1] ^ xm) * 65537u + xc;
+    out[j] = __byte_perm(t0, t1, 0x7632);
+  }
+}
+
 template <int KIND>
 __device__ __forceinline__ void demod_regs(const uint32_t (&iq)[32], int sgn, uint32_t (&out)[16])
 {
@@ -146,9 +156,13 @@ __device__ __forceinline__ void demod_regs(const uint32_t (&iq)[32], int sgn, ui
   }
 }
 
+// BQ: BqStage = all five SMLAW products of a stage as IMAD.HI; BqStageH = the three input-side products as exact DFMA.RM on the
+// FP64 pipe (msdr_device.cuh).  Alone in its sub-partition a warp steps equally fast either way (43 cycles, it is issue-bound);
+// here two biquad warps, two epilogue warps and a converter share a sub-partition and the integer multiplier is the scarce pipe
+// (IMAD.HI occupies it for 5 cycles), so the default moves three of the five products off it.
+template <class BQ>
 __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
 {
-  using BQ = BqStage;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023u) & ~(uintptr_t)1023u);
   const uint32_t K = p.tc_K, KS = K / 32, ring = p.tc_ring;
@@ -163,8 +177,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
   if (tid == 0) {
     for (int i = 0; i < RS; ++i) { mbar_init(&pc->raw_full[i], 32); mbar_init(&pc->raw_free[i], 4); }
     for (int i = 0; i < RING_MAX; ++i) { mbar_init(&pc->a_full[i], 4); mbar_init(&pc->blk_free[i], 1); }
-    mbar_init(&pc->tmem_full, 1);
-    mbar_init(&pc->tmem_empty, kEpiWarps);
+    for (int b = 0; b < 2; ++b) { mbar_init(&pc->tmem_full[b], 1); mbar_init(&pc->tmem_empty[b], kEpiWarps); }
     mbar_init(&pc->b_full, 4);
     mbar_init(&pc->b_free, 1);
     for (int s = 0; s < NS; ++s) {
@@ -187,61 +200,47 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
 
   if (warp == kLoadWarp) {
     // ================================================================== raw rows: global -> staging ring
+    // lane -> (row r0 + 4 i, 16-byte chunk c): a warp instruction copies four rows of 128 bytes.  The 32 row offsets of a lane live
+    // in registers (in 16-byte units, so 2^20 rows x any stride fit 32 bits): the copy loop is an address add and a cp.async.
     Prof prof(p.prof, 5);
     uint32_t pseq = 0;
     const int r0 = lane >> 3, c = lane & 7;
+    const uint32_t stride16 = (uint32_t)(p.stride >> 3);
+    const uint4 *in16 = reinterpret_cast<const uint4 *>(p.in);
     for (uint32_t rb = blockIdx.x; rb < n_rb; rb += gridDim.x) {
       const uint32_t *rmap = p.tc_rowmap + (size_t)rb * M;
+      uint32_t rows[M / 4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) pc->rowmap_ld[lane + 32 * i] = __ldg(rmap + lane + 32 * i);
-      __syncwarp();
+      for (int i = 0; i < M / 4; ++i) rows[i] = __ldg(rmap + r0 + 4 * i);
       for (int j = -(int)(KS - 1); j < (int)NT; ++j, ++pseq) {
         const uint32_t stage = pseq % RS;
         prof.start();
-        mbar_wait(&pc->raw_free[stage], ((pseq / RS) & 1u) ^ 1u);
+        mbar_wait(&pc->raw_free[stage], ((pseq / RS) & 1u) ^ 1u, 256);
         prof.lap(0);
-        const long long s = (long long)j * N + 8 * c; // first sample of this lane's 16-byte chunk (negative: history)
         const uint32_t dst0 = smem_u32(sRaw + stage * kRawStageBytes) + (uint32_t)r0 * RAWP + (uint32_t)c * 16u;
-        if (!(p.ablate & 1u)) {
-#pragma unroll 8
+        if (p.ablate & 1u) {
+        } else if (j >= 0) {
+          const uint32_t col16 = (uint32_t)j * (N / 8) + (uint32_t)c; // this lane's chunk of the tile, in 16-byte units
+#pragma unroll
           for (int i = 0; i < M / 4; ++i) {
-            const uint32_t row = pc->rowmap_ld[r0 + 4 * i];
-            const bool valid = row != kPad && s >= -(long long)Hs;
-            const int16_t *src = p.in; // never dereferenced when the copy size is 0 (zero fill)
-            if (valid) src = s >= 0 ? p.in + (size_t)row * p.stride + s : p.hist + ((size_t)p.ch0 + row) * p.H + (Hs + s);
+            const bool valid = rows[i] != kPad;
+            const uint4 *src = in16 + ((size_t)(valid ? rows[i] : 0u) * stride16 + col16);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + (uint32_t)i * 4u * RAWP), "l"(src), "r"(valid ? 16 : 0) : "memory");
+          }
+        } else { // in front of sample 0: the carried history, or zeros beyond the taps' reach
+          const int s = j * N + 8 * c; // first sample of this lane's chunk (negative)
+#pragma unroll
+          for (int i = 0; i < M / 4; ++i) {
+            const bool valid = rows[i] != kPad && s >= -Hs;
+            const int16_t *src = valid ? p.hist + ((size_t)p.ch0 + rows[i]) * p.H + (Hs + s) : p.in; // never dereferenced when the size is 0
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + (uint32_t)i * 4u * RAWP), "l"(src), "r"(valid ? 16 : 0) : "memory");
           }
         }
         asm volatile("cp.async.mbarrier.arrive.noinc.shared.b64 [%0];" ::"r"(smem_u32(&pc->raw_full[stage])) : "memory");
         prof.lap(1);
       }
-      // carry the last H raw samples of every row: hist <- tail of (hist || in[0..L)).  This row block's reads of the old history
-      // were its first copies; they have landed once all of this lane's copies have.
-      asm volatile("cp.async.wait_all;" ::: "memory");
-      __syncwarp();
-      const uint32_t hq = p.H >> 3; // uint4 per history row (<= 33)
-      for (int r = 0; r < M; ++r) {
-        const uint32_t row = pc->rowmap_ld[r];
-        if (row == kPad) continue;
-        uint4 *hrow = reinterpret_cast<uint4 *>(p.hist + ((size_t)p.ch0 + row) * p.H);
-        const uint4 *irow = reinterpret_cast<const uint4 *>(p.in + (size_t)row * p.stride);
-        uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
-        const uint32_t i0 = (uint32_t)lane, i1 = (uint32_t)lane + 32u;
-        if (p.L >= p.H) {
-          const uint4 *src = irow + ((p.L - p.H) >> 3);
-          if (i0 < hq) v0 = src[i0];
-          if (i1 < hq) v1 = src[i1];
-        } else {
-          const uint32_t lq = p.L >> 3, keep = hq - lq; // keep = old entries that survive
-          if (i0 < hq) v0 = (i0 < keep) ? __ldcg(hrow + i0 + lq) : irow[i0 - keep];
-          if (i1 < hq) v1 = (i1 < keep) ? __ldcg(hrow + i1 + lq) : irow[i1 - keep];
-        }
-        __syncwarp();
-        if (i0 < hq) hrow[i0] = v0;
-        if (i1 < hq) hrow[i1] = v1;
-      }
-      prof.lap(2);
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
     prof.flush();
   } else if (warp >= kConv0 && warp < kConv0 + 4) {
     // ================================================================== byte planes: staging ring -> ring of A operands
@@ -251,7 +250,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
     for (uint32_t rb = blockIdx.x; rb < n_rb; rb += gridDim.x, ++nblk) {
       { // Toeplitz operand of this row block's table; the previous row block's MMAs must be done with the old one
         const uint32_t set = __ldg(&p.tc_rb[rb].x);
-        mbar_wait(&pc->b_free, (nblk & 1u) ^ 1u);
+        mbar_wait(&pc->b_free, (nblk & 1u) ^ 1u, 128);
         const uint4 *src = reinterpret_cast<const uint4 *>(p.tc_bmat + (size_t)set * 4 * b_plane);
         uint4 *dst = reinterpret_cast<uint4 *>(sB);
         for (uint32_t i = r; i < 4 * b_plane / 16; i += M) dst[i] = __ldg(src + i);
@@ -262,9 +261,9 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
       for (uint32_t u = 0; u < npairs; ++u, ++pseq) {
         const uint32_t stage = pseq % RS, pos = pseq % ring;
         prof.start();
-        mbar_wait(&pc->raw_full[stage], (pseq / RS) & 1u);
+        mbar_wait(&pc->raw_full[stage], (pseq / RS) & 1u, 128);
         prof.lap(0);
-        mbar_wait(&pc->blk_free[pos], ((pseq / ring) & 1u) ^ 1u);
+        mbar_wait(&pc->blk_free[pos], ((pseq / ring) & 1u) ^ 1u, 128);
         prof.lap(1);
         if (!(p.ablate & 1u)) {
           const uint32_t a = smem_u32(sRaw + stage * kRawStageBytes) + r * RAWP;
@@ -279,6 +278,29 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
         if (lane == 0) { mbar_arrive(&pc->a_full[pos]); mbar_arrive(&pc->raw_free[stage]); }
         prof.lap(2);
       }
+      { // carry the last H raw samples of this thread's row: hist <- tail of (hist || in[0..L)).  The old history was this row
+        // block's first staging entries, which this thread converted long ago; nobody else reads or writes the row's history.
+        const uint32_t row = __ldg(p.tc_rowmap + (size_t)rb * M + r);
+        if (row != kPad) {
+          const uint32_t hq = p.H >> 3; // uint4 per history row (<= 33)
+          uint4 *hrow = reinterpret_cast<uint4 *>(p.hist + ((size_t)p.ch0 + row) * p.H);
+          const uint4 *irow = reinterpret_cast<const uint4 *>(p.in + (size_t)row * p.stride);
+          if (p.L >= p.H) {
+            const uint4 *src = irow + ((p.L - p.H) >> 3);
+            for (uint32_t i0 = 0; i0 < hq; i0 += 4) { // four loads in flight
+              uint4 v[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) if (i0 + k < hq) v[k] = __ldg(src + i0 + k);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) if (i0 + k < hq) hrow[i0 + k] = v[k];
+            }
+          } else { // a short update: part of the old history survives (moved down in increasing order, never onto unread entries)
+            const uint32_t lq = p.L >> 3, keep = hq - lq;
+            for (uint32_t i = 0; i < keep; ++i) hrow[i] = __ldcg(hrow + i + lq);
+            for (uint32_t i = keep; i < hq; ++i) hrow[i] = __ldg(irow + (i - keep));
+          }
+        }
+      }
     }
     prof.flush();
   } else if (warp == kMmaWarp) {
@@ -292,13 +314,18 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
       for (uint32_t t = 0; t < NT; ++t, ++tseq) {
         const uint32_t qt = qbase + t + KS - 1; // newest pair of this tile's window
         prof.start();
-        mbar_wait(&pc->a_full[qt % ring], (qt / ring) & 1u);
+        mbar_wait(&pc->a_full[qt % ring], (qt / ring) & 1u, 32);
         prof.lap(0);
-        mbar_wait(&pc->tmem_empty, (tseq & 1u) ^ 1u);
-        prof.lap(1);
-        tc_fence_after();
-        if (!(p.ablate & 1u)) issue_tile(ictx, tmem, qt, KS, ring);
-        umma_commit(&pc->tmem_full);
+        // the two branches have their own accumulators and their own hand-off: the epilogue drains I while Q is being issued, and
+        // the next tile's I products start as soon as I is drained
+#pragma unroll
+        for (uint32_t br = 0; br < 2; ++br) {
+          mbar_wait(&pc->tmem_empty[br], (tseq & 1u) ^ 1u, 32);
+          if (br == 0) prof.lap(1);
+          tc_fence_after();
+          if (!(p.ablate & 1u)) issue_branch(ictx, tmem, qt, KS, ring, br);
+          umma_commit(&pc->tmem_full[br]);
+        }
         umma_commit(&pc->blk_free[(qt - (KS - 1)) % ring]); // the oldest pair of the window is not read again
         prof.lap(2);
       }
@@ -322,17 +349,16 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
         const uint32_t slot = tseq % NS;
         uint32_t iq[32];
         prof.start();
-        mbar_wait(&pc->tmem_full, tseq & 1u);
+        mbar_wait(&pc->tmem_full[0], tseq & 1u, 48);
         prof.lap(0);
         tc_fence_after();
         if (!(p.ablate & 1u)) {
 #pragma unroll
           for (int b = 0; b < 4; ++b) {
-            uint32_t ai[8], aq[8];
+            uint32_t ai[8];
             drain8(lane_addr + (uint32_t)(8 * b), ai);
-            drain8(lane_addr + (uint32_t)(kAccPerBranch * N + 8 * b), aq);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) iq[8 * b + j] = pack_sat_iq((int)ai[j] >> 15, (int)aq[j] >> 15);
+            for (int j = 0; j < 8; ++j) iq[8 * b + j] = (uint32_t)((int)ai[j] >> 15); // saturated together with Q below
           }
         } else {
 #pragma unroll
@@ -340,13 +366,27 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&pc->tmem_empty); // the next tile's MMAs overlap the demodulation
+        if (lane == 0) mbar_arrive(&pc->tmem_empty[0]); // the next tile's I products may start
+        mbar_wait(&pc->tmem_full[1], tseq & 1u, 48);
+        tc_fence_after();
+        if (!(p.ablate & 1u)) {
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            uint32_t aq[8];
+            drain8(lane_addr + (uint32_t)(kAccPerBranch * N + 8 * b), aq);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) iq[8 * b + j] = pack_sat_iq((int)iq[8 * b + j], (int)aq[j] >> 15);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&pc->tmem_empty[1]);
         prof.lap(1);
         uint32_t out[16];
-        if (kind <= 1) demod_regs<0>(iq, kind ? 1 : -1, out);
+        if (kind <= 1) demod_ssb_regs(iq, kind ? 0u : 0xFFFF0000u, kind ? 0u : 0x10000u, out);
         else if (kind == 2) demod_regs<2>(iq, 0, out);
         else demod_regs<3>(iq, 0, out);
-        mbar_wait(&pc->slot_free[slot], ((tseq / NS) & 1u) ^ 1u);
+        mbar_wait(&pc->slot_free[slot], ((tseq / NS) & 1u) ^ 1u, 128);
         prof.lap(2);
         const uint32_t ya = smem_u32(sY + slot * kSlotBytes) + trow * (uint32_t)(YW * 4) + (uint32_t)(half * 64);
 #pragma unroll
@@ -386,7 +426,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
       for (uint32_t t = 0; t < NT; ++t, ++tseq) {
         const uint32_t slot = tseq % NS, phs = (tseq / NS) & 1u;
         prof.start();
-        mbar_wait(isA ? &pc->y_full[slot][q] : &pc->ab_full[slot][q], phs);
+        mbar_wait(isA ? &pc->y_full[slot][q] : &pc->ab_full[slot][q], phs, 128);
         prof.lap(0);
         const uint32_t ya = smem_u32(sY + slot * kSlotBytes) + trow * (uint32_t)(YW * 4);
         if (!(p.ablate & 2u) && active) {
@@ -409,27 +449,32 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
     }
     prof.flush();
   } else if (warp == kStoreWarp) {
-    // ================================================================== final audio: slot -> `out`
+    // ================================================================== final audio: slot -> `out` (row offsets in registers like the loader)
     Prof prof(p.prof, 6);
     const int r0 = lane >> 3, c = lane & 7;
+    const uint32_t stride16 = (uint32_t)(p.stride >> 3);
+    uint4 *out16 = reinterpret_cast<uint4 *>(p.out);
     uint32_t tseq = 0;
     for (uint32_t rb = blockIdx.x; rb < n_rb; rb += gridDim.x) {
       const uint32_t *rmap = p.tc_rowmap + (size_t)rb * M;
+      uint32_t rows[M / 4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) pc->rowmap_st[lane + 32 * i] = __ldg(rmap + lane + 32 * i);
-      __syncwarp();
+      for (int i = 0; i < M / 4; ++i) rows[i] = __ldg(rmap + r0 + 4 * i);
       for (uint32_t t = 0; t < NT; ++t, ++tseq) {
         const uint32_t slot = tseq % NS, phs = (tseq / NS) & 1u;
         prof.start();
-        mbar_wait(&pc->st_full[slot], phs);
+        mbar_wait(&pc->st_full[slot], phs, 256);
         prof.lap(0);
         const uint32_t sa = smem_u32(sY + slot * kSlotBytes) + (uint32_t)r0 * (uint32_t)(YW * 4) + (uint32_t)c * 16u;
-        int16_t *gcol = p.out + (size_t)t * N + (size_t)c * 8;
-#pragma unroll 8
-        for (int i = 0; i < M / 4; ++i) {
-          const uint32_t row = pc->rowmap_st[r0 + 4 * i];
-          const uint4 v = lds128(sa + (uint32_t)i * 4u * (uint32_t)(YW * 4));
-          if (row != kPad) *reinterpret_cast<uint4 *>(gcol + (size_t)row * p.stride) = v;
+        const uint32_t col16 = t * (N / 8) + (uint32_t)c;
+#pragma unroll
+        for (int i0 = 0; i0 < M / 4; i0 += 4) {
+          uint4 v[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) v[k] = lds128(sa + (uint32_t)(i0 + k) * 4u * (uint32_t)(YW * 4));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (rows[i0 + k] != kPad) out16[(size_t)rows[i0 + k] * stride16 + col16] = v[k];
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&pc->slot_free[slot]);
@@ -458,11 +503,14 @@ cudaError_t launch_chain_v5(const ChainParams &p_in, cudaStream_t stream, int va
   ChainParams p = p_in;
   p.ablate = ((uint32_t)variant >> 4) & 3u;
   const size_t smem = smem_bytes(p.tc_K, p.tc_ring);
-  cudaError_t e = cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // study knobs: variant bit 0 = all five products as IMAD.HI, bit 1 = feed-forward products as DFMA; default = IMAD.WIDE for the
+  // four products off the recurrence
+  auto kern = (variant & 1) ? chain_kernel<BqStage> : (variant & 2) ? chain_kernel<BqStageH> : chain_kernel<BqStageW>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const uint32_t grid = p.n_items < (uint32_t)sms ? p.n_items : (uint32_t)sms;
   if (info) { info->grid = (int)grid; info->block = kThreads; info->smem = smem; info->tile = tc::N; }
-  chain_kernel<<<grid, kThreads, smem, stream>>>(p);
+  kern<<<grid, kThreads, smem, stream>>>(p);
   return cudaGetLastError();
 }
 

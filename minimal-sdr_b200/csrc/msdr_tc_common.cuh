@@ -115,6 +115,24 @@ __device__ __forceinline__ void issue_tile(const IssueCtx &c, uint32_t tmem, uin
   }
 }
 
+// The MMAs of ONE branch of a tile (msdr_chain_v5.cu hands the two branches to the epilogue separately).
+__device__ __forceinline__ void issue_branch(const IssueCtx &c, uint32_t tmem, uint32_t qt, uint32_t KS, uint32_t ring, uint32_t br)
+{
+  uint32_t pos = (qt - (KS - 1)) % ring;
+  const uint32_t d0 = tmem + (br * kAccPerBranch) * N;
+  for (uint32_t ks = 0; ks < KS; ++ks) {
+    const uint64_t aoff = (uint64_t)((pos * kPairBytes) >> 4), boff = (uint64_t)((ks * 2 * kKStrideB) >> 4);
+    const uint32_t acc = ks > 0;
+    const uint64_t a_hi = c.descA[2 * br] + aoff, a_lo = c.descA[2 * br + 1] + aoff; // hi planes are signed bytes, lo planes unsigned
+    const uint64_t b_hi = c.descB[2 * br] + boff, b_lo = c.descB[2 * br + 1] + boff;
+    umma_i8(d0, a_hi, b_hi, 1, 1, acc);
+    umma_i8(d0 + N, a_hi, b_lo, 1, 0, acc);
+    umma_i8(d0 + N, a_lo, b_hi, 0, 1, 1);
+    umma_i8(d0 + 2 * N, a_lo, b_lo, 0, 0, acc);
+    pos = pos + 1 == ring ? 0 : pos + 1;
+  }
+}
+
 // Epilogue step 1 (thread = TMEM lane = channel row): accumulators -> recombine -> >>15 -> SSAT16 (arm_fir_fast_q15.c:234-238)
 // -> packed (I | Q << 16) parked in this thread's staging row.  cvt.pack.sat saturates and packs both branches at once.
 __device__ __forceinline__ uint32_t pack_sat_iq(int I, int Q)
