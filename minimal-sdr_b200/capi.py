@@ -46,7 +46,8 @@ class AnrState(C.Structure):  # msdr_anr_state
 
 
 def lib_path():
-    return os.path.join(_HERE, "csrc", "libmsdr.so")
+    # MSDR_LIBMSDR: developer aid, another build of the same library (kernel tuning experiments: tools/build_variant.sh)
+    return os.environ.get("MSDR_LIBMSDR") or os.path.join(_HERE, "csrc", "libmsdr.so")
 
 
 _lib = None

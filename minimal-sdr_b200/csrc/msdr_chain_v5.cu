@@ -47,6 +47,13 @@ constexpr uint32_t kRawStageBytes = M * RAWP;
 constexpr uint32_t kSlotBytes = M * YW * 4;
 constexpr uint32_t kCtrlBytes = 1024;
 constexpr uint32_t kPad = 0xFFFFFFFFu;
+// sleep between mbarrier probes per role (nanoseconds; msdr_device.cuh::mbar_wait).  The tensor-memory hand-off between the MMA warp
+// and the epilogue is the kernel's tightest loop and probes often; everything that sits behind a ring of slots can afford to find
+// out late that its barrier has flipped, and its probes otherwise delay the dependent instruction chains of the biquad warps.
+#ifndef MSDR_V5_NS
+#define MSDR_V5_NS 1
+#endif
+constexpr uint32_t kNsLoad = 256 * MSDR_V5_NS, kNsConv = 128 * MSDR_V5_NS, kNsSlot = 128 * MSDR_V5_NS, kNsBq = 128 * MSDR_V5_NS, kNsStore = 256 * MSDR_V5_NS;
 
 struct __align__(16) Ctrl {
   uint64_t raw_full[RS];        // load -> convert    : the stage's copies have landed (32 arrivals, cp.async.mbarrier.arrive.noinc)
@@ -215,7 +222,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
       for (int j = -(int)(KS - 1); j < (int)NT; ++j, ++pseq) {
         const uint32_t stage = pseq % RS;
         prof.start();
-        mbar_wait(&pc->raw_free[stage], ((pseq / RS) & 1u) ^ 1u, 256);
+        mbar_wait(&pc->raw_free[stage], ((pseq / RS) & 1u) ^ 1u, kNsLoad);
         prof.lap(0);
         const uint32_t dst0 = smem_u32(sRaw + stage * kRawStageBytes) + (uint32_t)r0 * RAWP + (uint32_t)c * 16u;
         if (p.ablate & 1u) {
@@ -250,7 +257,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
     for (uint32_t rb = blockIdx.x; rb < n_rb; rb += gridDim.x, ++nblk) {
       { // Toeplitz operand of this row block's table; the previous row block's MMAs must be done with the old one
         const uint32_t set = __ldg(&p.tc_rb[rb].x);
-        mbar_wait(&pc->b_free, (nblk & 1u) ^ 1u, 128);
+        mbar_wait(&pc->b_free, (nblk & 1u) ^ 1u, kNsConv);
         const uint4 *src = reinterpret_cast<const uint4 *>(p.tc_bmat + (size_t)set * 4 * b_plane);
         uint4 *dst = reinterpret_cast<uint4 *>(sB);
         for (uint32_t i = r; i < 4 * b_plane / 16; i += M) dst[i] = __ldg(src + i);
@@ -261,9 +268,9 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
       for (uint32_t u = 0; u < npairs; ++u, ++pseq) {
         const uint32_t stage = pseq % RS, pos = pseq % ring;
         prof.start();
-        mbar_wait(&pc->raw_full[stage], (pseq / RS) & 1u, 128);
+        mbar_wait(&pc->raw_full[stage], (pseq / RS) & 1u, kNsConv);
         prof.lap(0);
-        mbar_wait(&pc->blk_free[pos], ((pseq / ring) & 1u) ^ 1u, 128);
+        mbar_wait(&pc->blk_free[pos], ((pseq / ring) & 1u) ^ 1u, kNsConv);
         prof.lap(1);
         if (!(p.ablate & 1u)) {
           const uint32_t a = smem_u32(sRaw + stage * kRawStageBytes) + r * RAWP;
@@ -386,7 +393,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
         if (kind <= 1) demod_ssb_regs(iq, kind ? 0u : 0xFFFF0000u, kind ? 0u : 0x10000u, out);
         else if (kind == 2) demod_regs<2>(iq, 0, out);
         else demod_regs<3>(iq, 0, out);
-        mbar_wait(&pc->slot_free[slot], ((tseq / NS) & 1u) ^ 1u, 128);
+        mbar_wait(&pc->slot_free[slot], ((tseq / NS) & 1u) ^ 1u, kNsSlot);
         prof.lap(2);
         const uint32_t ya = smem_u32(sY + slot * kSlotBytes) + trow * (uint32_t)(YW * 4) + (uint32_t)(half * 64);
 #pragma unroll
@@ -426,7 +433,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
       for (uint32_t t = 0; t < NT; ++t, ++tseq) {
         const uint32_t slot = tseq % NS, phs = (tseq / NS) & 1u;
         prof.start();
-        mbar_wait(isA ? &pc->y_full[slot][q] : &pc->ab_full[slot][q], phs, 128);
+        mbar_wait(isA ? &pc->y_full[slot][q] : &pc->ab_full[slot][q], phs, kNsBq);
         prof.lap(0);
         const uint32_t ya = smem_u32(sY + slot * kSlotBytes) + trow * (uint32_t)(YW * 4);
         if (!(p.ablate & 2u) && active) {
@@ -463,7 +470,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
       for (uint32_t t = 0; t < NT; ++t, ++tseq) {
         const uint32_t slot = tseq % NS, phs = (tseq / NS) & 1u;
         prof.start();
-        mbar_wait(&pc->st_full[slot], phs, 256);
+        mbar_wait(&pc->st_full[slot], phs, kNsStore);
         prof.lap(0);
         const uint32_t sa = smem_u32(sY + slot * kSlotBytes) + (uint32_t)r0 * (uint32_t)(YW * 4) + (uint32_t)c * 16u;
         const uint32_t col16 = t * (N / 8) + (uint32_t)c;
@@ -505,7 +512,7 @@ cudaError_t launch_chain_v5(const ChainParams &p_in, cudaStream_t stream, int va
   const size_t smem = smem_bytes(p.tc_K, p.tc_ring);
   // study knobs: variant bit 0 = all five products as IMAD.HI, bit 1 = feed-forward products as DFMA; default = IMAD.WIDE for the
   // four products off the recurrence
-  auto kern = (variant & 1) ? chain_kernel<BqStage> : (variant & 2) ? chain_kernel<BqStageH> : chain_kernel<BqStageW>;
+  auto kern = (variant & 1) ? chain_kernel<BqStage> : (variant & 2) ? chain_kernel<BqStageH> : (variant & 4) ? chain_kernel<BqStageC> : chain_kernel<BqStageW>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const uint32_t grid = p.n_items < (uint32_t)sms ? p.n_items : (uint32_t)sms;
