@@ -173,24 +173,30 @@ __device__ __forceinline__ uint32_t bq_word(BqStageD (&st)[NS], uint32_t w)
 template <int NS>
 __device__ __forceinline__ uint32_t bq_word(BqStageH (&st)[NS], uint32_t w)
 {
-  static_assert(NS == 1, "the hybrid stage is used one stage per warp");
   int xe, xo; // prmt selector bit 3 replicates the sign of the selected byte: one instruction per sign extension
   asm("prmt.b32 %0, %1, 0, 0x9910;" : "=r"(xe) : "r"(w));
   asm("prmt.b32 %0, %1, 0, 0xBB32;" : "=r"(xo) : "r"(w));
-  const int ye = bq_step(st[0], xe);
-  const int yo = bq_step(st[0], xo);
+  int ye = bq_step(st[0], xe);
+#pragma unroll
+  for (int k = 1; k < NS; ++k) ye = bq_step(st[k], ye >> 16); // stages take the int16 value, hand on y << 16
+  int yo = bq_step(st[0], xo);
+#pragma unroll
+  for (int k = 1; k < NS; ++k) yo = bq_step(st[k], yo >> 16);
   return __byte_perm((uint32_t)ye, (uint32_t)yo, 0x7632);
 }
 
 template <int NS>
 __device__ __forceinline__ uint32_t bq_word(BqStageC (&st)[NS], uint32_t w)
 {
-  static_assert(NS == 1, "the chained hybrid stage is used one stage per warp");
   int xe, xo; // prmt selector bit 3 replicates the sign of the selected byte: one instruction per sign extension
   asm("prmt.b32 %0, %1, 0, 0x9910;" : "=r"(xe) : "r"(w));
   asm("prmt.b32 %0, %1, 0, 0xBB32;" : "=r"(xo) : "r"(w));
-  const int ye = bq_step(st[0], xe);
-  const int yo = bq_step(st[0], xo);
+  int ye = bq_step(st[0], xe);
+#pragma unroll
+  for (int k = 1; k < NS; ++k) ye = bq_step(st[k], ye >> 16); // stages take the int16 value, hand on y << 16
+  int yo = bq_step(st[0], xo);
+#pragma unroll
+  for (int k = 1; k < NS; ++k) yo = bq_step(st[k], yo >> 16);
   return __byte_perm((uint32_t)ye, (uint32_t)yo, 0x7632);
 }
 __device__ __forceinline__ void bq_load_stage(BqStageC &s, uint32_t &flag, const int32_t *__restrict__ bq, uint32_t Cpad, int obj, int stage, uint32_t ch)
@@ -210,6 +216,38 @@ __device__ __forceinline__ void bq_store_stage(const BqStageC &s, uint32_t flag,
   int32_t *b = bq + (size_t)((obj * 4 + stage) * 8) * Cpad + ch;
   b[5 * (size_t)Cpad] = (int32_t)(((uint32_t)bq_int_from_d(s.x1) << 16) | ((uint32_t)bq_int_from_d(s.x2) & 0xFFFFu));
   b[6 * (size_t)Cpad] = (int32_t)bq_pack_hist(s.y1, s.y2);
+  b[7 * (size_t)Cpad] = (int32_t)((uint32_t)s.res | flag);
+}
+
+template <int NS>
+__device__ __forceinline__ uint32_t bq_word(BqStageE (&st)[NS], uint32_t w)
+{
+  int xe, xo;
+  asm("prmt.b32 %0, %1, 0, 0x9910;" : "=r"(xe) : "r"(w));
+  asm("prmt.b32 %0, %1, 0, 0xBB32;" : "=r"(xo) : "r"(w));
+#pragma unroll
+  for (int k = 0; k < NS; ++k) xe = bq_step(st[k], xe);
+#pragma unroll
+  for (int k = 0; k < NS; ++k) xo = bq_step(st[k], xo);
+  return __byte_perm((uint32_t)xe, (uint32_t)xo, 0x5410);
+}
+__device__ __forceinline__ void bq_load_stage(BqStageE &s, uint32_t &flag, const int32_t *__restrict__ bq, uint32_t Cpad, int obj, int stage, uint32_t ch)
+{
+  const int32_t *b = bq + (size_t)((obj * 4 + stage) * 8) * Cpad + ch;
+  bq_set_coefs(s, __ldcg(b + 0 * (size_t)Cpad), __ldcg(b + 1 * (size_t)Cpad), __ldcg(b + 2 * (size_t)Cpad), __ldcg(b + 3 * (size_t)Cpad),
+               __ldcg(b + 4 * (size_t)Cpad));
+  const uint32_t w5 = (uint32_t)__ldcg(b + 5 * (size_t)Cpad), w6 = (uint32_t)__ldcg(b + 6 * (size_t)Cpad);
+  s.x1 = bq_d_from_int((int)w5 >> 16); s.x2 = bq_d_from_int((int)(short)(w5 & 0xFFFFu));
+  s.y1 = bq_d_from_int((int)w6 >> 16); s.y2 = bq_d_from_int((int)(short)(w6 & 0xFFFFu));
+  const uint32_t w7 = (uint32_t)__ldcg(b + 7 * (size_t)Cpad);
+  s.res = (int)(w7 & 0x3FFFu);
+  flag = w7 & 0x80000000u;
+}
+__device__ __forceinline__ void bq_store_stage(const BqStageE &s, uint32_t flag, int32_t *__restrict__ bq, uint32_t Cpad, int obj, int stage, uint32_t ch)
+{
+  int32_t *b = bq + (size_t)((obj * 4 + stage) * 8) * Cpad + ch;
+  b[5 * (size_t)Cpad] = (int32_t)(((uint32_t)bq_int_from_d(s.x1) << 16) | ((uint32_t)bq_int_from_d(s.x2) & 0xFFFFu));
+  b[6 * (size_t)Cpad] = (int32_t)(((uint32_t)bq_int_from_d(s.y1) << 16) | ((uint32_t)bq_int_from_d(s.y2) & 0xFFFFu));
   b[7 * (size_t)Cpad] = (int32_t)((uint32_t)s.res | flag);
 }
 
