@@ -204,6 +204,7 @@ int msdr_anr_create(msdr_anr **out, int device, uint32_t n_channels)
     std::vector<float> l(cp, 120.0f), n(cp, 0.001f); // .ino:715,718
     e = cudaMemcpy(anr->d_lidx, l.data(), cp * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(anr->d_ngamma, n.data(), cp * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize(); // legacy-stream copies / memsets vs this object's non-blocking stream
   }
   if (e == cudaSuccess) e = cudaFuncSetAttribute(msdr::anr::anr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msdr::anr::kSmem);
   if (e != cudaSuccess) {
@@ -275,6 +276,7 @@ int msdr_anr_update(msdr_anr *anr, int mode, int16_t *data, uint32_t n_blocks, s
     anr->stage_samples = need;
   }
   ACK(cudaMemcpy2DAsync(anr->d_data, L * 2, data, stride * 2, L * 2, anr->C, cudaMemcpyHostToDevice, anr->stream));
+  ACK(cudaDeviceSynchronize()); // the copies ran in the legacy stream; this object's stream is non-blocking
   int st = msdr_anr_update_device(anr, mode, anr->d_data, n_blocks, L);
   if (st != MSDR_OK) return st;
   ACK(cudaMemcpy2DAsync(data, stride * 2, anr->d_data, L * 2, L * 2, anr->C, cudaMemcpyDeviceToHost, anr->stream));
@@ -305,6 +307,7 @@ int msdr_anr_set_state(msdr_anr *anr, uint32_t ch, const msdr_anr_state *in)
   ACK(cudaMemcpy(anr->d_lidx + ch, &in->lidx, 4, cudaMemcpyHostToDevice));
   ACK(cudaMemcpy(anr->d_ngamma + ch, &in->ngamma, 4, cudaMemcpyHostToDevice));
   ACK(cudaMemcpy(anr->d_in_idx + ch, &in->in_idx, 4, cudaMemcpyHostToDevice));
+  ACK(cudaDeviceSynchronize()); // the copies ran in the legacy stream; this object's stream is non-blocking
   return MSDR_OK;
 }
 

@@ -290,7 +290,7 @@ int msdr_chain_create(msdr_chain **out, int device, uint32_t n_channels, uint32_
   CKC(cudaMalloc(&chain->d_hist, (size_t)n_channels * chain->H * sizeof(int16_t)));
   CKC(cudaMalloc(&chain->d_bq, (size_t)kBqWords * chain->Cpad * sizeof(int32_t)));
   CKC(cudaMalloc(&chain->d_pll, (size_t)3 * chain->Cpad * sizeof(float)));
-  CKC(cudaMemset(chain->d_pll, 0, (size_t)3 * chain->Cpad * sizeof(float)));
+  CKC(cudaMemsetAsync(chain->d_pll, 0, (size_t)3 * chain->Cpad * sizeof(float), chain->own_stream));
   CKC(cudaMalloc(&chain->d_sets, (size_t)MSDR_MAX_FIR_SETS * chain->set_stride_words * sizeof(int32_t)));
   CKC(cudaMalloc(&chain->d_set_kp4, MSDR_MAX_FIR_SETS * sizeof(uint32_t)));
   CKC(cudaMalloc(&chain->d_ctrl, (size_t)(1 + chain->Cpad / kGroup + 1) * sizeof(int)));
@@ -388,6 +388,7 @@ int msdr_chain_set_anr(msdr_chain *chain, uint32_t ch0, uint32_t nch, int anr_on
     std::vector<float> l(cp, 120.0f), g(cp, 0.001f); // Minimal-SDR.ino:715,718
     CK(cudaMemcpy(chain->d_anr_lidx, l.data(), cp * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(chain->d_anr_ngamma, g.data(), cp * 4, cudaMemcpyHostToDevice));
+    CK(cudaDeviceSynchronize()); // legacy-stream copies / memsets vs the chain's non-blocking stream
   }
   for (uint32_t c = ch0; c < ch0 + nch; ++c) {
     chain->n_anr += (anr_on != 0) - (chain->h_anr[c] != 0);
@@ -424,6 +425,7 @@ int msdr_chain_set_anr_state(msdr_chain *chain, uint32_t ch, const msdr_anr_stat
   CK(cudaMemcpy(chain->d_anr_lidx + ch, &in->lidx, 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(chain->d_anr_ngamma + ch, &in->ngamma, 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(chain->d_anr_idx + ch, &in->in_idx, 4, cudaMemcpyHostToDevice));
+  CK(cudaDeviceSynchronize()); // legacy-stream copies vs the chain's non-blocking stream
   return MSDR_OK;
 }
 
@@ -632,11 +634,15 @@ int build_tc_plan(msdr_chain *chain, uint32_t ch0, uint32_t nch, uint32_t sms, b
   }
   CK(cudaMalloc(&pl.d_rowmap, rowmap.size() * 4)); CK(cudaMalloc(&pl.d_grp, std::max<size_t>(grp.size(), 1) * 4));
   CK(cudaMalloc(&pl.d_wave_rb0, wave_rb0.size() * 4)); CK(cudaMalloc(&pl.d_rb, rbs.size() * sizeof(uint4))); CK(cudaMalloc(&pl.d_bmat, bm.size()));
-  CK(cudaMemcpy(pl.d_rowmap, rowmap.data(), rowmap.size() * 4, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(pl.d_grp, grp.data(), grp.size() * 4, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(pl.d_wave_rb0, wave_rb0.data(), wave_rb0.size() * 4, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(pl.d_rb, rbs.data(), rbs.size() * sizeof(uint4), cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(pl.d_bmat, bm.data(), bm.size(), cudaMemcpyHostToDevice));
+  CK(cudaMemcpyAsync(pl.d_rowmap, rowmap.data(), rowmap.size() * 4, cudaMemcpyHostToDevice, chain->stream));
+  CK(cudaMemcpyAsync(pl.d_grp, grp.data(), grp.size() * 4, cudaMemcpyHostToDevice, chain->stream));
+  CK(cudaMemcpyAsync(pl.d_wave_rb0, wave_rb0.data(), wave_rb0.size() * 4, cudaMemcpyHostToDevice, chain->stream));
+  CK(cudaMemcpyAsync(pl.d_rb, rbs.data(), rbs.size() * sizeof(uint4), cudaMemcpyHostToDevice, chain->stream));
+  CK(cudaMemcpyAsync(pl.d_bmat, bm.data(), bm.size(), cudaMemcpyHostToDevice, chain->stream));
+  // On the chain's stream, NOT cudaMemcpy: a synchronous copy from pageable memory returns once the data is staged, its DMA runs in
+  // the legacy stream, and the chain's stream is non-blocking - a kernel launched right after could read the plan before it had
+  // arrived (seen as intermittent mismatches in the last, ragged channel chunk of msdr_chain_update).
+  CK(cudaStreamSynchronize(chain->stream));
   pl.usable = true;
   return MSDR_OK;
 }
@@ -1099,6 +1105,7 @@ int msdr_chain_set_state(msdr_chain *chain, uint32_t ch, const msdr_channel_stat
   CK(cudaMemcpy2D(chain->d_bq + ch, (size_t)chain->Cpad * sizeof(int32_t), in->biquad_definition, sizeof(int32_t), sizeof(int32_t), kBqWords,
                   cudaMemcpyHostToDevice));
   CK(cudaMemcpy2D(chain->d_pll + ch, (size_t)chain->Cpad * sizeof(float), in->syncam_pll, sizeof(float), sizeof(float), 3, cudaMemcpyHostToDevice));
+  CK(cudaDeviceSynchronize()); // legacy-stream copies vs the chain's non-blocking stream
   return MSDR_OK;
 }
 

@@ -247,6 +247,7 @@ int msdr_frontend_create(msdr_frontend **out, int device, uint32_t n_channels, f
     s.mult = msdr::fe::amp_multiplier(agc_start);     // .ino:385
   }
   e = cudaMemcpy(fe->d_state, h.data(), h.size() * sizeof(msdr::fe::State), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize(); // legacy-stream copy vs this object's non-blocking stream
   if (e != cudaSuccess) { g_fe_error = std::string("frontend_create: ") + cudaGetErrorString(e); cudaFree(fe->d_state); delete fe; return MSDR_ERR_CUDA; }
   *out = fe;
   return MSDR_OK;
@@ -288,6 +289,7 @@ int msdr_frontend_preset(msdr_frontend *fe, uint32_t ch0, uint32_t nch, uint16_t
   FCK(cudaMemcpy(h.data(), fe->d_state + ch0, nch * sizeof(msdr::fe::State), cudaMemcpyDeviceToHost));
   for (auto &s : h) { s.hpf_x1 = (int32_t)((uint32_t)first_reading << 14); s.hpf_y1 = 0; }
   FCK(cudaMemcpy(fe->d_state + ch0, h.data(), nch * sizeof(msdr::fe::State), cudaMemcpyHostToDevice));
+  FCK(cudaDeviceSynchronize()); // the copies ran in the legacy stream; this object's stream is non-blocking
   return MSDR_OK;
 }
 
@@ -326,6 +328,7 @@ int msdr_frontend_update(msdr_frontend *fe, const uint16_t *adc, int16_t *out, u
     fe->stage_samples = need;
   }
   FCK(cudaMemcpy2DAsync(fe->d_in, L * 2, adc, stride * 2, L * 2, fe->C, cudaMemcpyHostToDevice, fe->stream));
+  FCK(cudaDeviceSynchronize()); // the copies ran in the legacy stream; this object's stream is non-blocking
   int st = msdr_frontend_update_device(fe, fe->d_in, fe->d_out, n_blocks, L);
   if (st != MSDR_OK) return st;
   FCK(cudaMemcpy2DAsync(out, stride * 2, fe->d_out, L * 2, L * 2, fe->C, cudaMemcpyDeviceToHost, fe->stream));
@@ -355,6 +358,7 @@ int msdr_frontend_set_state(msdr_frontend *fe, uint32_t ch, const msdr_frontend_
   FCK(cudaSetDevice(fe->device));
   FCK(cudaStreamSynchronize(fe->stream));
   FCK(cudaMemcpy(fe->d_state + ch, in, sizeof(*in), cudaMemcpyHostToDevice));
+  FCK(cudaDeviceSynchronize()); // the copies ran in the legacy stream; this object's stream is non-blocking
   return MSDR_OK;
 }
 

@@ -142,6 +142,7 @@ int msdr_syncam_create(msdr_syncam **out, int device, uint32_t n_channels)
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&sc->own_stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaMalloc(&sc->d_state, (size_t)3 * sc->Cpad * 4);
   if (e == cudaSuccess) e = cudaMemset(sc->d_state, 0, (size_t)3 * sc->Cpad * 4); // fil_out = omega2 = phzerror = 0, .ino:643-645
+  if (e == cudaSuccess) e = cudaDeviceSynchronize(); // legacy-stream memset vs this object's non-blocking stream
   if (e != cudaSuccess) {
     g_sc_error = std::string("syncam_create: ") + cudaGetErrorString(e);
     cudaFree(sc->d_state);
@@ -204,6 +205,7 @@ int msdr_syncam_update(msdr_syncam *sc, const int16_t *I, const int16_t *Q, int1
   int16_t *dI = sc->d_buf, *dQ = sc->d_buf + need, *dO = sc->d_buf + 2 * need;
   SCK(cudaMemcpy2DAsync(dI, L * 2, I, stride * 2, L * 2, sc->C, cudaMemcpyHostToDevice, sc->stream));
   SCK(cudaMemcpy2DAsync(dQ, L * 2, Q, stride * 2, L * 2, sc->C, cudaMemcpyHostToDevice, sc->stream));
+  SCK(cudaDeviceSynchronize()); // the copies ran in the legacy stream; this object's stream is non-blocking
   int st = msdr_syncam_update_device(sc, dI, dQ, dO, n_blocks, L);
   if (st != MSDR_OK) return st;
   SCK(cudaMemcpy2DAsync(out, stride * 2, dO, L * 2, L * 2, sc->C, cudaMemcpyDeviceToHost, sc->stream));
@@ -230,6 +232,7 @@ int msdr_syncam_set_state(msdr_syncam *sc, uint32_t ch, float fil_out, float ome
   SCK(cudaMemcpy(sc->d_state + ch, &fil_out, 4, cudaMemcpyHostToDevice));
   SCK(cudaMemcpy(sc->d_state + sc->Cpad + ch, &omega2, 4, cudaMemcpyHostToDevice));
   SCK(cudaMemcpy(sc->d_state + 2 * (size_t)sc->Cpad + ch, &phzerror, 4, cudaMemcpyHostToDevice));
+  SCK(cudaDeviceSynchronize()); // the copies ran in the legacy stream; this object's stream is non-blocking
   return MSDR_OK;
 }
 
