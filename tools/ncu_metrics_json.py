@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Turn `ncu -i X.ncu-rep --page raw --csv` into the small JSON bench.py reads for roofline.traffic.
-usage: python tools/ncu_metrics_json.py raw.csv out.json "<how the capture was made>"
+usage: python tools/ncu_metrics_json.py raw.csv out.json "<how the capture was made>" [algorithmic bytes of the captured launch]
 """
 import csv
 import json
@@ -12,7 +12,9 @@ KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
         "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic", "sm__cycles_elapsed.avg",
-        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__t_sector_hit_rate.pct"]
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__t_sector_hit_rate.pct",
+        "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"]
 UNIT = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
 
 
@@ -37,6 +39,9 @@ def main():
         dram.append(tot)
     out = {"source": sys.argv[3] if len(sys.argv) > 3 else "", "kernel": kernel, "launches": launches,
            "dram_bytes_per_launch": sum(dram) / max(1, len(dram))}
+    if len(sys.argv) > 4:  # 4 B per sample x samples of the captured launch: bench.py pairs `traffic` with THIS, not with its own average launch
+        out["algorithmic_bytes_per_launch"] = float(sys.argv[4])
+        out["traffic_over_algorithmic"] = out["dram_bytes_per_launch"] / out["algorithmic_bytes_per_launch"]
     json.dump(out, open(sys.argv[2], "w"), indent=1)
     print(json.dumps({k: out[k] for k in ("kernel", "dram_bytes_per_launch")}))
 
