@@ -7,9 +7,11 @@
  * arm_copy_q15.c / arm_sqrt_q31.c / filter_biquad.cpp (see oracle/Makefile); tests/test_oracle_vs_ref.py
  * checks this file against it bit-for-bit, and tests/golden/ holds vectors generated from it
  * (tests/golden/make_golden.py).  The reference repository ships no tests or golden vectors of its own.
- * Exception — orc_freq_conv: the reference's freq_conv.cpp calls arm_mult_q15/arm_add_q15/arm_sub_q15,
- * which are NOT vendored in the reference (CMSIS-DSP V1.5.1, prebuilt on Teensy) => parity unpinned
- * for that one function; it restates the documented CMSIS semantics.
+ * orc_freq_conv: the reference's freq_conv.cpp calls arm_mult_q15/arm_add_q15/arm_sub_q15, which are NOT vendored in
+ * the reference (CMSIS-DSP V1.5.1, prebuilt on Teensy).  It is pinned against the reference's own freq_conv.cpp compiled
+ * with those three routines built from the saturating primitives the reference DOES vendor as portable C
+ * (clip_q31_to_q15, __QADD16, __QSUB16: oracle/ref_q15_prims.c, oracle/ref_freq_conv.cpp); what stays unpinned is the
+ * three one-line element loops around those primitives, restated from the CMSIS documentation.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this
  * library.  The product (minimal-sdr_b200/) never links or calls it and has no CPU fallback.
@@ -223,8 +225,9 @@ void orc_biquad_update(orc_biquad *b, int16_t *block, uint32_t n /* even; 128 in
 }
 
 /* ------------------------------------------------------------------------------------------------
- * A6  AudioEffectFreqConv::update, freq_conv.cpp:30-116 (dead code in the sketch).  PARITY UNPINNED:
- * arm_mult_q15 = ssat16((a*b)>>15), arm_add_q15 / arm_sub_q15 saturating (CMSIS-DSP V1.5.1 docs).
+ * A6  AudioEffectFreqConv::update, freq_conv.cpp:30-116 (dead code in the sketch).  arm_mult_q15 = ssat16((a*b)>>15),
+ * arm_add_q15 / arm_sub_q15 saturating (CMSIS-DSP V1.5.1 docs); checked against the reference's own class compiled with the
+ * vendored primitives (tests/test_oracle_vs_ref.py::test_freq_conv_matches_reference_class; see the file header).
  * pass == 0 forwards the inputs unchanged (freq_conv.cpp:49-56; note the inverted naming).
  */
 static inline int16_t orc_mult_q15(int16_t a, int16_t b) { return (int16_t)orc_ssat16(((int32_t)a * b) >> 15); }
