@@ -237,7 +237,8 @@ def workload_config(args, w, C, world):
         cfg["channels_per_gpu"] = C
         cfg["channels_total"] = w.channels if w.scaling == "strong" else C * world
     if getattr(args, "with_frontend", False):
-        cfg["with_frontend"] = "raw 12-bit ADC codes through msdr_frontend_update_device (DC-block, amplifier, AGC) before every chain update"
+        cfg["with_frontend"] = ("raw 12-bit ADC codes through msdr_frontend_update_device (DC-block, amplifier, AGC) before every chain update; where the chain "
+                                "leaves SMs free the front end of batch k+1 runs on them beside the chain of batch k (two streams), else the kernels alternate")
     return cfg
 
 
@@ -288,6 +289,7 @@ def main():
     ap.add_argument("--with-frontend", action="store_true",
                     help="study: feed raw 12-bit ADC codes through the front-end conditioning kernel (DC-block, amplifier, AGC; SURVEY 8f rank 1) "
                          "in front of every chain update; the default line measures the north-star path only")
+    ap.add_argument("--frontend-serial", action="store_true", help="with --with-frontend: front end and chain alternate on one stream (no overlap)")
     ap.add_argument("--layout", choices=["updates", "rows"], default="updates",
                     help="device-resident input layout: 'updates' = one contiguous [channels][samples] batch per update (how a streaming "
                          "receiver holds its block batches), 'rows' = one row per channel for the whole step, updates are column windows of it")
@@ -359,20 +361,43 @@ def main():
     torch.cuda.synchronize()
 
     fe = None
+    fe_pipelined = False
     if args.with_frontend:
         fe = m.Frontend(C, device=local_rank)
-        fe.set_stream(stream.cuda_stream)
         adc = [(a[:, :nb * BLOCK].to(torch.int32) // 16 + 2048).clamp_(0, 4095).to(torch.int16).contiguous() for a, b, nb, st in dev_calls]
         adc_calls = [(a.data_ptr(), a.stride(0)) for a in adc]
         fe_in = [torch.empty_like(a) for a in adc]  # conditioned IF samples, the chain's input in this mode
         calls = [(f.data_ptr(), c[1], c[2], f.stride(0)) for f, c in zip(fe_in, calls)]
+        # Few channels leave SMs without a chain to pin (4096 channels = 128 groups on 148 SMs).  Then the chain kernel gives those SMs
+        # up ("spare_sms"), the front end packs its channel groups onto them ("sms") and conditions block batch k + 1 on its own stream
+        # while the chain works on batch k.  Otherwise (or with --frontend-serial) the two kernels alternate on one stream.
+        n_sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        spare = n_sms - (C + 31) // 32
+        fe_pipelined = spare >= 8 and not args.frontend_serial
+        if fe_pipelined:
+            stream_fe = torch.cuda.Stream(device=dev)
+            fe.set_stream(stream_fe.cuda_stream)
+            fe.set_option("sms", spare)
+            g.set_option("spare_sms", spare)
+            ev_fe = [torch.cuda.Event() for _ in calls]
+            ev_chain = [torch.cuda.Event() for _ in calls]
+        else:
+            fe.set_stream(stream.cuda_stream)
         torch.cuda.synchronize()
 
     def step():
         for i, (d_in, d_out, nb, stride) in enumerate(calls):
             if fe is not None:  # raw codes -> conditioned IF samples
-                fe.update_device(adc_calls[i][0], d_in, nb, stride)
+                if fe_pipelined:
+                    stream_fe.wait_event(ev_chain[i])  # the chain has read this batch's previous contents (no-op before the first record)
+                    fe.update_device(adc_calls[i][0], d_in, nb, stride)
+                    ev_fe[i].record(stream_fe)
+                    stream.wait_event(ev_fe[i])
+                else:
+                    fe.update_device(adc_calls[i][0], d_in, nb, stride)
             g.update_device(d_in, d_out, nb, stride)
+            if fe_pipelined:
+                ev_chain[i].record(stream)
 
     def barrier():
         if world > 1:

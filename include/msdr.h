@@ -156,6 +156,8 @@ int msdr_chain_set_state(msdr_chain *chain, uint32_t ch, const msdr_channel_stat
  *   512  never run two chain sets per SM
  *   +16 / +32: ablation (skip the FIR / the biquad arithmetic; results are wrong, timing only)
  * "timing" (CUDA events around each update), "host_chunk_channels", "host_chunk_blocks" (msdr_chain_update pipelining).
+ * "spare_sms" = n: the chain kernel for few channels launches n fewer CTAs than there are SMs (never fewer than it has channel groups
+ * to pin), leaving those SMs to a kernel on another stream, e.g. the front end of the next block batch (msdr_frontend_set_option "sms").
  * Environment, developer aids: MSDR_VARIANT (default variant of new chains), MSDR_PROF (per-role cycle counters on stderr). */
 int msdr_chain_set_option(msdr_chain *chain, const char *key, int value);
 
@@ -229,6 +231,10 @@ int msdr_frontend_update_device(msdr_frontend *fe, const uint16_t *d_adc, int16_
 int msdr_frontend_get_state(msdr_frontend *fe, uint32_t ch, msdr_frontend_state *out);
 int msdr_frontend_set_state(msdr_frontend *fe, uint32_t ch, const msdr_frontend_state *in);
 uint64_t msdr_frontend_launch_count(const msdr_frontend *fe);
+/* "sms" = n > 0: run the conditioning kernel in about n CTAs of several warps (one per SM) instead of one small CTA per 32 channels
+ * spread over the whole GPU, so that it can run BESIDE a receive chain that leaves SMs free (msdr_chain_set_option "spare_sms"):
+ * conditioning of block batch k+1 on one stream while the chain works on batch k on another.  0 = spread (default). */
+int msdr_frontend_set_option(msdr_frontend *fe, const char *key, int value);
 /* AudioAmplifier::gain (mixer.h:75-79): clamp to +-32767, multiplier = (int32_t)(gain * 65536.0f) */
 int32_t msdr_amp_gain_multiplier(float gain);
 /* AudioAmplifier::update / applyGain (mixer.cpp:34-47,134-159) in place on host rows: SSAT16((multipliers[row] * x) >> 16).

@@ -102,6 +102,7 @@ SYMBOLS = {
     "msdr_frontend_get_state": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(FrontendState)]),
     "msdr_frontend_set_state": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(FrontendState)]),
     "msdr_frontend_launch_count": (C.c_uint64, [C.c_void_p]),
+    "msdr_frontend_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "msdr_amp_gain_multiplier": (C.c_int32, [C.c_float]),
     "msdr_op_dac_codes": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_size_t]),
     "msdr_op_amplifier": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_size_t]),

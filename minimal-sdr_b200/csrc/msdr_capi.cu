@@ -134,6 +134,7 @@ struct msdr_chain {
 
   int variant = 0;
   uint32_t host_chunk_channels = 0, host_chunk_blocks = 0; // 0 = auto
+  uint32_t spare_sms = 0;
   uint64_t launches = 0;
   std::string err;
   ChainLaunchInfo last_info{};
@@ -775,6 +776,7 @@ int msdr_chain_update_range_device(msdr_chain *chain, uint32_t ch0, uint32_t nch
   p.n_sets = (uint32_t)chain->sets.size(); p.set_stride_words = chain->set_stride_words;
   p.ctrl = chain->d_ctrl;
   p.am_q31 = (chain->flags & MSDR_FLAG_AM_Q31) ? 1u : 0u;
+  p.spare_sms = chain->spare_sms;
   const uint32_t NG = (nch + kGroup - 1) / kGroup;
   const size_t n_flags = (size_t)NG * ((p.L + chain_tile_samples() - 1) / chain_tile_samples());
   if (n_flags > chain->tile_flags_len || chain->epoch >= 0x7FFFFFF0u) { // (re)allocate zeroed flags; epochs restart
@@ -1061,6 +1063,7 @@ int msdr_chain_set_option(msdr_chain *chain, const char *key, int value)
   if (!strcmp(key, "timing")) { chain->timed = value != 0; return MSDR_OK; }
   if (!strcmp(key, "host_chunk_channels")) { chain->host_chunk_channels = (uint32_t)value; return MSDR_OK; }
   if (!strcmp(key, "host_chunk_blocks")) { chain->host_chunk_blocks = (uint32_t)value; return MSDR_OK; }
+  if (!strcmp(key, "spare_sms")) { chain->spare_sms = value < 0 ? 0u : (uint32_t)value; return MSDR_OK; }
   return fail(chain, MSDR_ERR_ARGUMENT, std::string("unknown option ") + key);
 }
 

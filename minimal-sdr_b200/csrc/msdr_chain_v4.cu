@@ -896,7 +896,12 @@ cudaError_t launch_chain_v4(const ChainParams &p_in, cudaStream_t stream, int va
             : shape == 3 ? chain_kernel<false, false, true> : chain_kernel<false, false, false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  const uint32_t grid = shape == 3 ? p.W / 2 : p.W; // p.W = chains per wave; the DUAL shape runs two per CTA
+  uint32_t grid = shape == 3 ? p.W / 2 : p.W; // p.W = chains per wave; the DUAL shape runs two per CTA
+  if (shape != 3 && p.spare_sms) { // leave SMs to a kernel on another stream; CTA b pins groups b, b + W, ...: every group below W needs its CTA
+    const uint32_t need = p.NG < p.W ? p.NG : p.W;
+    const uint32_t want = p.W > p.spare_sms ? p.W - p.spare_sms : 1u;
+    grid = want > need ? want : need;
+  }
   if (info) { info->grid = (int)grid; info->block = kThreads; info->smem = smem; info->tile = SPAN; }
   kern<<<grid, kThreads, smem, stream>>>(p);
   return cudaGetLastError();

@@ -14,6 +14,8 @@
 #include "msdr_internal.h"
 #include "../../include/msdr.h"
 
+#include <cstring>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -97,15 +99,19 @@ struct Params {
 
 // Shared memory decides how many of these one-warp CTAs an SM holds: the blocks travel in pieces of kPart samples through a
 // ring of kNBuf buffers (64 samples, three deep: 13.8 KB per CTA, 16 CTAs per SM).
+// The warps of a CTA are independent (only __syncwarp): blockDim.x / 32 > 1 packs several channel groups onto one SM, which confines
+// the kernel to a few SMs so that a chain kernel that leaves SMs free can run beside it (msdr_frontend_set_option "sms").
 template <int kPart, int kNBuf>
-__global__ void __launch_bounds__(32) frontend_kernel(const Params p)
+__global__ void frontend_kernel(const Params p)
 {
   constexpr int kPartPitchW = kPart / 2 + 4;     // 4 mod 32, conflict-free row-wise 128-bit access
   constexpr int RPI = 512 / (kPart * 2);         // rows per warp instruction
   constexpr int CPR = 32 / RPI;                  // 16-byte chunks per row
-  __shared__ __align__(16) uint32_t buf[kNBuf][kGroup * kPartPitchW];
-  const int lane = threadIdx.x;
-  const uint32_t g = blockIdx.x, row = g * kGroup + lane;
+  extern __shared__ __align__(16) uint32_t fe_smem[];
+  uint32_t (*buf)[kGroup * kPartPitchW] = reinterpret_cast<uint32_t (*)[kGroup * kPartPitchW]>(fe_smem + (size_t)(threadIdx.x >> 5) * kNBuf * kGroup * kPartPitchW);
+  const int lane = threadIdx.x & 31;
+  const uint32_t g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), row = g * kGroup + lane;
+  if (g * kGroup >= p.C) return; // a warp past the last channel group (whole warps only: nothing below is block-wide)
   const bool active = row < p.C;
   const int nrows = min(kGroup, (int)(p.C - g * kGroup));
   State s;
@@ -212,6 +218,7 @@ struct msdr_frontend {
   int16_t *d_out = nullptr;
   size_t stage_samples = 0;
   uint64_t launches = 0;
+  int sms = 0; // option "sms": > 0 = pack the channel groups into about this many CTAs of several warps (one per SM)
   std::string err;
 };
 
@@ -306,7 +313,16 @@ int msdr_frontend_update_device(msdr_frontend *fe, const uint16_t *d_adc, int16_
   p.agc_max = fe->agc_max; p.agc_on = fe->agc_on;
   // piece length / ring depth measured at 65 536 and 262 144 channels (profiles/r01_frontend.txt): <64, 3> 1018 / 1189 Gsamples/s,
   // <128, 2> 914 / 1225, <64, 2> 1043 / 1153, <32, 4> 1040 / 1125, <32, 3> 1031 / 1027, <64, 4> 884 / 1195
-  msdr::fe::frontend_kernel<64, 3><<<(fe->C + msdr::kGroup - 1) / msdr::kGroup, 32, 0, fe->stream>>>(p);
+  {
+    constexpr int kPart = 64, kNBuf = 3;
+    const uint32_t groups = (fe->C + msdr::kGroup - 1) / msdr::kGroup;
+    const size_t warp_smem = (size_t)kNBuf * msdr::kGroup * (kPart / 2 + 4) * 4; // 13.8 KB per channel group
+    uint32_t wpc = 1;
+    if (fe->sms > 0) wpc = std::min<uint32_t>(16, std::max<uint32_t>(1, (groups + (uint32_t)fe->sms - 1) / (uint32_t)fe->sms));
+    auto kern = msdr::fe::frontend_kernel<kPart, kNBuf>;
+    if (wpc * warp_smem > 48 * 1024) FCK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(wpc * warp_smem)));
+    kern<<<(groups + wpc - 1) / wpc, 32 * wpc, wpc * warp_smem, fe->stream>>>(p);
+  }
   FCK(cudaGetLastError());
   fe->launches++;
   return MSDR_OK;
@@ -363,6 +379,13 @@ int msdr_frontend_set_state(msdr_frontend *fe, uint32_t ch, const msdr_frontend_
 }
 
 uint64_t msdr_frontend_launch_count(const msdr_frontend *fe) { return fe ? fe->launches : 0; }
+
+int msdr_frontend_set_option(msdr_frontend *fe, const char *key, int value)
+{
+  if (!fe || !key) return MSDR_ERR_ARGUMENT;
+  if (!strcmp(key, "sms")) { fe->sms = value < 0 ? 0 : value; return MSDR_OK; }
+  return fe_fail(fe, MSDR_ERR_ARGUMENT, std::string("unknown option ") + key);
+}
 
 int32_t msdr_amp_gain_multiplier(float gain) { return msdr::fe::amp_multiplier(gain); }
 

@@ -51,6 +51,7 @@ struct ChainParams {
   const uint8_t *tc_bmat;      // [n_sets][4 * 64 * K] Toeplitz operands
   uint32_t tc_K, tc_ring, tc_sub, tc_ff; // tc_ff: kernel shape 0/1/2 (msdr_chain_v4.cu: chain_v4_config)
   uint32_t NU;                 // readiness units per channel (v4)
+  uint32_t spare_sms;          // v4: launch this many fewer CTAs than a wave has slots (never fewer than there are chains to pin)
   long long *prof;             // developer profile buffer [grid][64] or NULL
   int *tile_cnt;               // [NG][NU] rows of group g whose unit u is in `out` (zeroed before the launch)
 };

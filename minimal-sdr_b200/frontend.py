@@ -61,6 +61,9 @@ class Frontend:
         h = 0 if cuda_stream is None else (int(cuda_stream) or 1)
         return self._ck(self._L.msdr_frontend_set_stream(self.h, C.c_void_p(h)))
 
+    def set_option(self, key, value):
+        return self._ck(self._L.msdr_frontend_set_option(self.h, key.encode(), int(value)))
+
     def synchronize(self):
         return self._ck(self._L.msdr_frontend_synchronize(self.h))
 

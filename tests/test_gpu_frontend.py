@@ -104,3 +104,29 @@ def test_dac_codes_and_amplifier_ops(msdr, forc):
     assert L.msdr_op_amplifier(0, msdr.capi.ptr(mults), msdr.capi.ptr(d), 8, 8192, 8192) == 0
     for r in range(8):
         assert np.array_equal(d[r], forc.amp_apply(s[r], int(mults[r]))[0]), r
+
+
+def test_packed_launch_and_spare_sms_change_nothing(msdr, forc, orc, K):
+    """The options behind the two-stream pipeline of bench.py --with-frontend: the front end packed into a few multi-warp CTAs
+    (msdr_frontend_set_option "sms") and the chain kernel leaving SMs free ("spare_sms") give the same bytes and the same state."""
+    C, nb = 300, 12   # 10 channel groups, the last one partial
+    codes = fl.adc_stream(C, 128 * nb, seed=17)
+    outs = []
+    for sms in (0, 3, 4, 1):   # 1 -> 10 groups in one CTA of 10 warps
+        g = msdr.Frontend(C)
+        g.set_option("sms", sms)
+        outs.append((g.update(codes[:, :128 * 5]), g.update(codes[:, 128 * 5:]), [g.get_state(c).multiplier for c in (0, 31, 32, 299)]))
+    o = forc.frontend(C)
+    yo = o.run(codes)
+    for a, b, st in outs:
+        assert_same(np.concatenate([a, b], axis=1), yo, "packed front end")
+        assert st == outs[0][2]
+    modes = msdr.synth.mixed_modes(4096)
+    x = msdr.synth.batch(modes[:64], 128 * 6)
+    ys = []
+    for spare in (0, 20, 147):
+        gch, och = configure_pair(msdr, orc, K, modes[:64])
+        gch.set_option("spare_sms", spare)
+        ys.append(gch.update(x))
+    assert_same(ys[0], och.run(x)[0], "spare_sms 0")
+    assert np.array_equal(ys[0], ys[1]) and np.array_equal(ys[0], ys[2])
