@@ -100,7 +100,8 @@ struct msdr_chain {
     uint64_t version = 0;
     uint32_t ch0 = 0, nch = 0, sms = 0, W = 0, K = 0, rings[4] = {0, 0, 0, 0}, n_rb = 0, n_waves = 0;
     bool usable = false, want_dual = false, dual = false;
-    uint32_t ring_v5 = 0; // msdr_chain_v5.cu: operand ring depth, 0 = the window does not fit that kernel
+    uint32_t ring_v5 = 0;  // msdr_chain_v5.cu: operand ring depth, 0 = the window does not fit that kernel
+    uint32_t ring_v5l = 0; // msdr_chain_v5l.cu (half-tile hand-offs, for the 256-tap window)
     uint32_t *d_rowmap = nullptr, *d_grp = nullptr, *d_wave_rb0 = nullptr;
     uint4 *d_rb = nullptr;
     uint8_t *d_bmat = nullptr;
@@ -591,6 +592,7 @@ int build_tc_plan(msdr_chain *chain, uint32_t ch0, uint32_t nch, uint32_t sms, b
   if (!chain_v4_config(K, smem_max, pl.rings)) { pl.usable = false; return MSDR_OK; }
   pl.K = K;
   pl.ring_v5 = chain_v5_config(K, smem_max);
+  pl.ring_v5l = chain_v5l_config(K, smem_max);
   pl.dual = want_dual && pl.rings[3] != 0;
   const uint32_t W = pl.W = sms * (pl.dual ? 2u : 1u);
 
@@ -811,21 +813,22 @@ int msdr_chain_update_range_device(msdr_chain *chain, uint32_t ch0, uint32_t nch
       uint32_t kp_live = 0;
       for (const FirSet &fs : chain->sets)
         if (fs.users) kp_live = std::max(kp_live, kp_of_taps(fs.T));
-      if (!chain_v5_config(tc_window_words_kp(kp_live), smem_max)) use_v5 = false;
+      if (!chain_v5_config(tc_window_words_kp(kp_live), smem_max) && !chain_v5l_config(tc_window_words_kp(kp_live), smem_max)) use_v5 = false;
     }
     const msdr_chain::TcPlan *plp = nullptr;
     int st = MSDR_OK;
     if (use_v5) { // a plan with ONE wave: rows sorted by table over the whole range (wave width = all groups)
       st = build_tc_plan(chain, ch0, nch, NG, false, &plp);
       if (st != MSDR_OK) return st;
-      if (!plp->usable || !plp->ring_v5) use_v5 = false; // window too long (256 taps): the chain kernel below
+      if (!plp->usable || (!plp->ring_v5 && !plp->ring_v5l)) use_v5 = false; // no row-block form fits this window: the chain kernel below
     }
     if (use_v5) {
       const msdr_chain::TcPlan &pl = *plp;
       p.NG = NG;
       p.n_items = pl.n_rb;
       p.tc_rowmap = pl.d_rowmap; p.tc_rb = pl.d_rb; p.tc_grp = pl.d_grp; p.tc_wave_rb0 = pl.d_wave_rb0; p.tc_bmat = pl.d_bmat;
-      p.tc_K = pl.K; p.tc_ring = pl.ring_v5;
+      const bool long_window = !pl.ring_v5 || ((chain->variant & 32768) && pl.ring_v5l); // 256 taps: the half-tile form (bit 15: study, any window)
+      p.tc_K = pl.K; p.tc_ring = long_window ? pl.ring_v5l : pl.ring_v5;
       if (chain->timed) {
         int stu = usage_resolve(chain);
         if (stu != MSDR_OK) return stu;
@@ -842,8 +845,13 @@ int msdr_chain_update_range_device(msdr_chain *chain, uint32_t ch0, uint32_t nch
         CK(cudaMemsetAsync(d_prof5, 0, (size_t)sms * 64 * sizeof(long long), chain->stream));
         p.prof = d_prof5;
       }
-      CK(launch_chain_v5(p, chain->stream, chain->variant, sms, &chain->last_info));
-      chain->last_kernel = "msdr::v5::chain_kernel (fused mix + tensor-core FIR pair + demod + biquad cascade; one CTA per 128-channel row block)";
+      if (long_window) {
+        CK(launch_chain_v5l(p, chain->stream, chain->variant, sms, &chain->last_info));
+        chain->last_kernel = "msdr::v5l::chain_kernel (fused mix + tensor-core FIR pair + demod + biquad cascade; one CTA per 128-channel row block, half-tile hand-offs for the long window)";
+      } else {
+        CK(launch_chain_v5(p, chain->stream, chain->variant, sms, &chain->last_info));
+        chain->last_kernel = "msdr::v5::chain_kernel (fused mix + tensor-core FIR pair + demod + biquad cascade; one CTA per 128-channel row block)";
+      }
       {
         int stl = syncam_lane_finish(chain, ch0, d_out, stride, p.L);
         if (stl != MSDR_OK) return stl;

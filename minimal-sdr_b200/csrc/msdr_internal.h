@@ -73,6 +73,9 @@ bool chain_v4_config(uint32_t K, int smem_max, uint32_t rings[4]);
 // row-block kernel for many channels (msdr_chain_v5.cu): p.n_items = number of row blocks, p.tc_ring from chain_v5_config (0 = does not fit)
 cudaError_t launch_chain_v5(const ChainParams &p, cudaStream_t stream, int variant, int sms, ChainLaunchInfo *info);
 uint32_t chain_v5_config(uint32_t K, int smem_max);
+// the same kernel with half-tile hand-offs for windows too long for it (256 taps; msdr_chain_v5l.cu)
+cudaError_t launch_chain_v5l(const ChainParams &p, cudaStream_t stream, int variant, int sms, ChainLaunchInfo *info);
+uint32_t chain_v5l_config(uint32_t K, int smem_max);
 
 // stage-level kernels on device buffers
 cudaError_t launch_mix_fs4(const int16_t *in, int16_t *I, int16_t *Q, uint32_t rows, uint32_t n, size_t stride, cudaStream_t s);

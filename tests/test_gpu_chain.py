@@ -167,8 +167,10 @@ def test_inplace_coefficient_rewrite_and_mode_change(msdr, orc, K):
         assert_same(a, b, w)
 
 
-def test_long_taps_256(msdr, orc, K):
-    """BASELINE config 4 shape: 255 taps + one zero (arm_fir_init_q15.c:55-64), 256-tap delay line."""
+@pytest.mark.parametrize("variant", [0, 4096, 4097])
+def test_long_taps_256(msdr, orc, K, variant):
+    """BASELINE config 4 shape: 255 taps + one zero (arm_fir_init_q15.c:55-64), 256-tap delay line.  variant 0: the chain kernel (few
+    channels); 4096 / 4097: the row-block kernel in its half-tile form for the long window (msdr_chain_v5l.cu), both stage forms."""
     rng = np.random.default_rng(44)
     modes = [AM, USB, LSB, CW] * 5
     c255 = rng.integers(-600, 600, 255).astype(np.int16)
@@ -177,8 +179,10 @@ def test_long_taps_256(msdr, orc, K):
     tabs = {c: (cI, cQ) if c % 2 else (wrap_coeffs(256, rng), wrap_coeffs(256, rng)) for c in range(len(modes))}
     x = np.stack([rng.integers(-32768, 32768, 128 * 16, dtype=np.int16) for _ in modes])
     g, o = configure_pair(msdr, orc, K, modes, max_taps=256, tables=tabs)
+    g.set_option("variant", variant)
     yg, yo = run_pair(g, o, x, splits=[1, 1, 2, 12])
     assert_same(yg, yo, "256 taps")
+    assert ("v5l" in g.last_kernel()) == bool(variant & 4096)
 
 
 def test_errors_match_reference_conventions(msdr, K):
