@@ -102,6 +102,9 @@ struct msdr_chain {
     bool usable = false, want_dual = false, dual = false;
     uint32_t ring_v5 = 0;  // msdr_chain_v5.cu: operand ring depth, 0 = the window does not fit that kernel
     uint32_t ring_v5l = 0; // msdr_chain_v5l.cu (half-tile hand-offs, for the 256-tap window)
+    uint32_t slots_v6 = 0, n_gb = 0; // msdr_chain_v6.cu: sub-tile slots (0 = the window does not fit), group blocks of 32 same-table rows
+    uint32_t *d_rowmap32 = nullptr;
+    uint4 *d_rb32 = nullptr;
     uint32_t *d_rowmap = nullptr, *d_grp = nullptr, *d_wave_rb0 = nullptr;
     uint4 *d_rb = nullptr;
     uint8_t *d_bmat = nullptr;
@@ -554,7 +557,7 @@ namespace {
 
 void free_tc_plan(msdr_chain::TcPlan &pl)
 {
-  cudaFree(pl.d_rowmap); cudaFree(pl.d_grp); cudaFree(pl.d_wave_rb0); cudaFree(pl.d_rb); cudaFree(pl.d_bmat);
+  cudaFree(pl.d_rowmap); cudaFree(pl.d_grp); cudaFree(pl.d_wave_rb0); cudaFree(pl.d_rb); cudaFree(pl.d_bmat); cudaFree(pl.d_rowmap32); cudaFree(pl.d_rb32);
   pl = msdr_chain::TcPlan{};
 }
 
@@ -593,6 +596,7 @@ int build_tc_plan(msdr_chain *chain, uint32_t ch0, uint32_t nch, uint32_t sms, b
   pl.K = K;
   pl.ring_v5 = chain_v5_config(K, smem_max);
   pl.ring_v5l = chain_v5l_config(K, smem_max);
+  pl.slots_v6 = chain_v6_config(K, smem_max);
   pl.dual = want_dual && pl.rings[3] != 0;
   const uint32_t W = pl.W = sms * (pl.dual ? 2u : 1u);
 
@@ -624,6 +628,22 @@ int build_tc_plan(msdr_chain *chain, uint32_t ch0, uint32_t nch, uint32_t sms, b
   }
   pl.n_rb = (uint32_t)rbs.size();
   pl.n_waves = (uint32_t)wave_rb0.size() - 1;
+  // msdr_chain_v6.cu: the whole range sorted by table and cut into group blocks of 32 rows (the last block of a table is padded)
+  std::vector<uint32_t> rowmap32;
+  std::vector<uint4> rbs32;
+  if (pl.slots_v6) {
+    const uint32_t G = chain_v6_group_rows();
+    for (auto &b : bucket) b.clear();
+    for (uint32_t r = 0; r < nch; ++r) bucket[chain->h_set[ch0 + r]].push_back(r);
+    for (uint32_t sid = 0; sid < n_sets; ++sid) {
+      const std::vector<uint32_t> &rows = bucket[sid];
+      for (size_t i0 = 0; i0 < rows.size(); i0 += G) {
+        for (size_t i = i0; i < i0 + G; ++i) rowmap32.push_back(i < rows.size() ? rows[i] : 0xFFFFFFFFu);
+        rbs32.push_back(make_uint4(sid, 0, 0, 0));
+      }
+    }
+    pl.n_gb = (uint32_t)rbs32.size();
+  }
 
   // Toeplitz operands of every live table for the common window K
   const size_t bsz = (size_t)4 * tc_tile_samples() * K;
@@ -642,6 +662,11 @@ int build_tc_plan(msdr_chain *chain, uint32_t ch0, uint32_t nch, uint32_t sms, b
   CK(cudaMemcpyAsync(pl.d_wave_rb0, wave_rb0.data(), wave_rb0.size() * 4, cudaMemcpyHostToDevice, chain->stream));
   CK(cudaMemcpyAsync(pl.d_rb, rbs.data(), rbs.size() * sizeof(uint4), cudaMemcpyHostToDevice, chain->stream));
   CK(cudaMemcpyAsync(pl.d_bmat, bm.data(), bm.size(), cudaMemcpyHostToDevice, chain->stream));
+  if (pl.n_gb) {
+    CK(cudaMalloc(&pl.d_rowmap32, rowmap32.size() * 4)); CK(cudaMalloc(&pl.d_rb32, rbs32.size() * sizeof(uint4)));
+    CK(cudaMemcpyAsync(pl.d_rowmap32, rowmap32.data(), rowmap32.size() * 4, cudaMemcpyHostToDevice, chain->stream));
+    CK(cudaMemcpyAsync(pl.d_rb32, rbs32.data(), rbs32.size() * sizeof(uint4), cudaMemcpyHostToDevice, chain->stream));
+  }
   // On the chain's stream, NOT cudaMemcpy: a synchronous copy from pageable memory returns once the data is staged, its DMA runs in
   // the legacy stream, and the chain's stream is non-blocking - a kernel launched right after could read the plan before it had
   // arrived (seen as intermittent mismatches in the last, ragged channel chunk of msdr_chain_update).
@@ -882,6 +907,71 @@ int msdr_chain_update_range_device(msdr_chain *chain, uint32_t ch0, uint32_t nch
     st = build_tc_plan(chain, ch0, nch, (uint32_t)sms, want_dual, &plp);
     if (st != MSDR_OK) return st;
     const msdr_chain::TcPlan &pl = *plp;
+    // Few channels: the time-folded kernel (msdr_chain_v6.cu), one CTA per 32 same-table channels, nothing leaves the SM.  Up to two
+    // group blocks per SM; beyond that the two chain sets per SM of msdr_chain_v4.cu (and then the row-block kernel) are faster.
+    // variant bit 16 forces it for any channel count (parity tests), bit 14 forbids it.
+    const bool use_v6 = pl.usable && pl.slots_v6 && !(chain->variant & (16384 | 128 | 256 | 512 | 2048)) &&
+                        ((chain->variant & 65536) || pl.n_gb <= 2u * (uint32_t)sms);
+    if (use_v6) {
+      p.NG = NG;
+      p.n_items = pl.n_gb;
+      p.tc_rowmap = pl.d_rowmap32; p.tc_rb = pl.d_rb32; p.tc_bmat = pl.d_bmat;
+      p.tc_K = pl.K; p.tc_ring = pl.slots_v6;
+      if (chain->timed) {
+        int stu = usage_resolve(chain);
+        if (stu != MSDR_OK) return stu;
+        CK(cudaEventRecord(chain->ev0, chain->stream));
+      }
+      {
+        int stl = syncam_lane_prepare(chain, ch0, nch, d_in, stride, p.L);
+        if (stl != MSDR_OK) return stl;
+      }
+      static const bool prof6 = getenv("MSDR_PROF") != nullptr;
+      long long *d_prof6 = nullptr;
+      if (prof6) {
+        CK(cudaMalloc(&d_prof6, (size_t)sms * 64 * sizeof(long long)));
+        CK(cudaMemsetAsync(d_prof6, 0, (size_t)sms * 64 * sizeof(long long), chain->stream));
+        p.prof = d_prof6;
+      }
+      const int sms_use = std::max(1, sms - (int)chain->spare_sms);
+      CK(launch_chain_v6(p, chain->stream, chain->variant, sms_use, &chain->last_info));
+      chain->last_kernel = "msdr::v6::chain_kernel (fused mix + tensor-core FIR pair + demod + biquad cascade; one CTA per 32-channel group block, tile rows folded over time)";
+      {
+        int stl = syncam_lane_finish(chain, ch0, d_out, stride, p.L);
+        if (stl != MSDR_OK) return stl;
+      }
+      if (chain->timed) {
+        CK(cudaEventRecord(chain->ev1, chain->stream));
+        chain->usage_pending = true;
+        chain->usage_blocks = n_blocks;
+      }
+      chain->launches++;
+      if (d_prof6) {
+        const uint32_t g = (uint32_t)chain->last_info.grid;
+        std::vector<long long> h((size_t)g * 64);
+        CK(cudaMemcpyAsync(h.data(), d_prof6, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, chain->stream));
+        CK(cudaStreamSynchronize(chain->stream));
+        cudaFree(d_prof6);
+        static const char *role[9] = {"convert", "mma", "epilogue", "chainA", "chainB", "load", "store", "ff1", "ff2"};
+        fprintf(stderr, "[msdr prof v6] grid %u, %u group blocks, mean cycles per CTA (counter 0..3):\n", g, pl.n_gb);
+        for (int r = 0; r < 9; ++r) {
+          double m[4] = {0, 0, 0, 0}, mx[4] = {0, 0, 0, 0};
+          for (uint32_t b = 0; b < g; ++b)
+            for (int i = 0; i < 4; ++i) { m[i] += (double)h[(size_t)b * 64 + r * 4 + i] / g; mx[i] = std::max(mx[i], (double)h[(size_t)b * 64 + r * 4 + i]); }
+          fprintf(stderr, "  %-9s %10.0f %10.0f %10.0f %10.0f   max %10.0f %10.0f %10.0f %10.0f\n", role[r], m[0], m[1], m[2], m[3], mx[0], mx[1], mx[2], mx[3]);
+        }
+        {
+          double c = 0, n = 0, cm = 0, nm = 0;
+          for (uint32_t b = 0; b < g; ++b) { c += (double)h[(size_t)b * 64 + 40] / g; n += (double)h[(size_t)b * 64 + 41] / g; cm = std::max(cm, (double)h[(size_t)b * 64 + 40]); nm = std::max(nm, (double)h[(size_t)b * 64 + 41]); }
+          fprintf(stderr, "  kernel entry -> chain B done: %.0f cycles, %.0f ns (mean); max %.0f cycles, %.0f ns\n", c, n, cm, nm);
+        }
+        if (getenv("MSDR_PROF_CTAS")) // per-CTA totals of chain A (wait, work) and the epilogue
+          for (uint32_t b = 0; b < g; ++b)
+            fprintf(stderr, "  cta %3u chainA %9lld %9lld  epilogue %9lld %9lld %9lld %9lld\n", b, h[(size_t)b * 64 + 12], h[(size_t)b * 64 + 13], h[(size_t)b * 64 + 8],
+                    h[(size_t)b * 64 + 9], h[(size_t)b * 64 + 10], h[(size_t)b * 64 + 11]);
+      }
+      return MSDR_OK;
+    }
     const bool dual = pl.dual; // false when the second set of chain slots does not fit next to this window (256 taps)
     use_tc = pl.usable;
     if (use_tc) {

@@ -73,6 +73,11 @@ bool chain_v4_config(uint32_t K, int smem_max, uint32_t rings[4]);
 // row-block kernel for many channels (msdr_chain_v5.cu): p.n_items = number of row blocks, p.tc_ring from chain_v5_config (0 = does not fit)
 cudaError_t launch_chain_v5(const ChainParams &p, cudaStream_t stream, int variant, int sms, ChainLaunchInfo *info);
 uint32_t chain_v5_config(uint32_t K, int smem_max);
+// pinned 32-channel group blocks with the tile rows folded over time (msdr_chain_v6.cu): p.tc_rowmap = [n_items][32] rows of one table,
+// p.tc_rb[i].x = table id, p.tc_ring = sub-tile slots from chain_v6_config (0 = the window does not fit)
+cudaError_t launch_chain_v6(const ChainParams &p, cudaStream_t stream, int variant, int sms, ChainLaunchInfo *info);
+uint32_t chain_v6_config(uint32_t K, int smem_max);
+uint32_t chain_v6_group_rows();
 // the same kernel with half-tile hand-offs for windows too long for it (256 taps; msdr_chain_v5l.cu)
 cudaError_t launch_chain_v5l(const ChainParams &p, cudaStream_t stream, int variant, int sms, ChainLaunchInfo *info);
 uint32_t chain_v5l_config(uint32_t K, int smem_max);

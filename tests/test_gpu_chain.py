@@ -302,7 +302,8 @@ def test_update_range_device(msdr, orc, K):
     assert_same(d_out.cpu().numpy(), yo, "range update")
 
 
-@pytest.mark.parametrize("variant,name", [(0, "default (tensor-core FIR, feed-forward helper warps)"), (2048, "tensor-core FIR + post warps"),
+@pytest.mark.parametrize("variant,name", [(0, "default (time-folded kernel, msdr_chain_v6.cu)"), (16384, "chain kernel (msdr_chain_v4.cu), feed-forward helper warps"),
+                                            (2048, "tensor-core FIR + post warps"),
                                             (256, "tensor-core FIR, inline epilogue"), (128, "helper warps, forced"), (64, "CUDA-core FIR (v3)"),
                                             (65, "v3, FP64 biquad"), (4096, "row-block kernel (msdr_chain_v5.cu), forced"),
                                             (4097, "row-block kernel, IMAD.HI stages"), (4098, "row-block kernel, DFMA feed-forward"),
@@ -328,6 +329,8 @@ def test_every_kernel_shape_is_bit_exact(msdr, orc, K, variant, name):
     assert o.fir_init(7, 2, cI, cQ) == 0
     yg, yo = run_pair(g, o, x, splits=[3, 1, 17, 2, 18])
     assert_same(yg, yo, name)
+    want = "v6::" if variant == 0 else "v5::" if variant & 4096 else "v3::" if variant & 64 else "v4::"
+    assert want in g.last_kernel(), (variant, g.last_kernel())
 
 
 def test_syncam_channels_in_a_chain(msdr, orc, K):
@@ -408,6 +411,18 @@ def test_anr_channels_in_a_chain(msdr, orc, K):
     assert_same(yg[exact], yo[exact], "chain with ANR channels")
     a, b = yg[9].astype(np.float64), yo[9].astype(np.float64)        # SYNCAM + notch: float tolerance
     assert np.abs(a - b).max() <= 3 and np.sqrt(np.mean((a - b) ** 2)) <= 1e-4 * np.sqrt(np.mean(b ** 2)) + 0.05
+
+
+def test_whole_file_on_the_chain_kernel():
+    """The time-folded kernel (msdr_chain_v6.cu) is the default for few channels, so this file runs on it; MSDR_VARIANT=16384 forbids it
+    and the chain tests run again on the chain kernel (msdr_chain_v4.cu), which still serves the channel counts between the two
+    other kernels and the 256-tap window at few channels."""
+    import subprocess
+    import sys
+    env = dict(os.environ, MSDR_VARIANT="16384")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-k",
+                        "not every_kernel_shape and not whole_file and not errors_match"], env=env, capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
 
 
 def test_whole_file_on_the_row_block_kernel():
