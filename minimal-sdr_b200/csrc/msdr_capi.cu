@@ -628,19 +628,47 @@ int build_tc_plan(msdr_chain *chain, uint32_t ch0, uint32_t nch, uint32_t sms, b
   }
   pl.n_rb = (uint32_t)rbs.size();
   pl.n_waves = (uint32_t)wave_rb0.size() - 1;
-  // msdr_chain_v6.cu: the whole range sorted by table and cut into group blocks of 32 rows (the last block of a table is padded)
+  // msdr_chain_v6.cu: the whole range sorted by table and cut into half blocks of 16 rows (the last one of a table is padded); a group
+  // block is two half blocks, each with its own table.  The envelope demodulators (AM, CW: a square root per sample) cost the
+  // epilogue several times what the SSB sums do and a CTA keeps its group block for the whole launch, so expensive halves are paired
+  // with cheap ones: every CTA then carries the same load (with whole blocks per table the AM / CW CTAs finish 7 % after the SSB ones).
   std::vector<uint32_t> rowmap32;
   std::vector<uint4> rbs32;
   if (pl.slots_v6) {
-    const uint32_t G = chain_v6_group_rows();
+    const uint32_t HR = chain_v6_group_rows() / 2;
+    struct Half { uint32_t sid; size_t i0; bool costly; };
+    std::vector<Half> costly, cheap;
     for (auto &b : bucket) b.clear();
     for (uint32_t r = 0; r < nch; ++r) bucket[chain->h_set[ch0 + r]].push_back(r);
     for (uint32_t sid = 0; sid < n_sets; ++sid) {
       const std::vector<uint32_t> &rows = bucket[sid];
-      for (size_t i0 = 0; i0 < rows.size(); i0 += G) {
-        for (size_t i = i0; i < i0 + G; ++i) rowmap32.push_back(i < rows.size() ? rows[i] : 0xFFFFFFFFu);
-        rbs32.push_back(make_uint4(sid, 0, 0, 0));
+      for (size_t i0 = 0; i0 < rows.size(); i0 += HR) {
+        bool env = false;
+        for (size_t i = i0; i < std::min(rows.size(), i0 + HR); ++i) {
+          const int md = chain->h_mode[ch0 + rows[i]];
+          env |= !(md == MSDR_MODE_LSB || md == MSDR_MODE_USB);
+        }
+        (env ? costly : cheap).push_back(Half{sid, i0, env});
       }
+    }
+    std::vector<Half> order; // costly and cheap halves alternate while both last; the rest follows in table order
+    size_t a = 0, b = 0;
+    while (a < costly.size() || b < cheap.size()) {
+      if (a < costly.size()) order.push_back(costly[a++]);
+      if (b < cheap.size()) order.push_back(cheap[b++]);
+    }
+    for (size_t h0 = 0; h0 < order.size(); h0 += 2) {
+      uint32_t sid2[2] = {order[h0].sid, order[h0].sid};
+      for (size_t h = h0; h < h0 + 2; ++h) {
+        if (h < order.size()) {
+          const std::vector<uint32_t> &rows = bucket[order[h].sid];
+          sid2[h - h0] = order[h].sid;
+          for (size_t i = order[h].i0; i < order[h].i0 + HR; ++i) rowmap32.push_back(i < rows.size() ? rows[i] : 0xFFFFFFFFu);
+        } else {
+          for (uint32_t i = 0; i < HR; ++i) rowmap32.push_back(0xFFFFFFFFu);
+        }
+      }
+      rbs32.push_back(make_uint4(sid2[0], sid2[1], 0, 0));
     }
     pl.n_gb = (uint32_t)rbs32.size();
   }

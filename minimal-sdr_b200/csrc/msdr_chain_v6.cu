@@ -30,6 +30,7 @@
 //   8        store     slot -> `out`
 // Chain A, chain B, FF1 and FF2 each have a sub-partition of their own; everything else is light (a CTA produces only what its own 32
 // channels consume).  DRAM traffic is the algorithmic 2 B in + 2 B out per sample.
+#include <cstdlib>
 #include "msdr_chain_v5_common.cuh"
 
 namespace msdr {
@@ -66,8 +67,8 @@ constexpr uint32_t kCtrlBytes = 1024;
 struct __align__(16) Ctrl {
   uint64_t raw_full[RS];          // load -> convert   : the stage's copies have landed (32 arrivals, cp.async.mbarrier.arrive.noinc)
   uint64_t raw_free[RS];          // convert -> load   : stage read (2 arrivals)
-  uint64_t a_full[4];             // convert -> MMA    : operand buffer [half][span parity] complete (2 arrivals)
-  uint64_t a_free[4];             // MMA -> convert    : the tile's MMAs are complete (tcgen05.commit)
+  uint64_t a_full[3];             // convert -> MMA    : operand buffer (tile number mod 3) complete (2 arrivals)
+  uint64_t a_free[3];             // MMA -> convert    : the tile's MMAs are complete (tcgen05.commit)
   uint64_t tmem_full[2];          // MMA -> epilogue   : accumulators of tile buffer b complete (tcgen05.commit)
   uint64_t tmem_empty[2];         // epilogue -> MMA   : drained (4 arrivals)
   uint64_t b_full, b_free;        // convert <-> MMA   : Toeplitz operand of the group block's table
@@ -83,12 +84,12 @@ struct __align__(16) Ctrl {
 };
 static_assert(sizeof(Ctrl) <= kCtrlBytes, "Ctrl must fit its smem slot");
 
-__host__ __device__ inline uint32_t units_per_buf(uint32_t K) { return 2u * (K / 32u) + 8u; } // history 2 KS - 2, new 8, one read past, one pad
+__host__ __device__ inline uint32_t units_per_buf(uint32_t K) { return 2u * (K / 32u) + 7u; } // history 2 KS - 2, new 8, one read past the end (times zero taps)
 __host__ __device__ inline uint32_t a_plane6(uint32_t K) { return units_per_buf(K) * kUnitBytes; }
 __host__ __device__ inline uint32_t b_plane6(uint32_t K) { return (uint32_t)NB * K; }
 size_t smem_bytes(uint32_t K, uint32_t nslot)
 {
-  return (size_t)kCtrlBytes + 16u * a_plane6(K) + 4u * b_plane6(K) + (size_t)RS * kRawStageBytes + 2u * kSpanBufBytes + (size_t)nslot * kSlotBytes + 1024u;
+  return (size_t)kCtrlBytes + 12u * a_plane6(K) + 8u * b_plane6(K) + (size_t)RS * kRawStageBytes + 2u * kSpanBufBytes + (size_t)nslot * kSlotBytes + 1024u;
 }
 
 __device__ __forceinline__ void umma_i8_n32(uint32_t dcol, uint64_t da, uint64_t db, uint32_t a_signed, uint32_t b_signed, uint32_t acc)
@@ -100,7 +101,11 @@ __device__ __forceinline__ void umma_i8_n32(uint32_t dcol, uint64_t da, uint64_t
       ::"r"(dcol), "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(0), "r"(0), "r"(0), "r"(0)
       : "memory");
 }
-// eight output columns of one branch: the three byte-plane accumulators (NB columns apart) -> the reference's accumulator mod 2^32
+// eight output columns of one branch: the three byte-plane accumulators (NB columns apart) -> the reference's accumulator mod 2^32.
+// Every sub-partition's integer multiplier is the busiest pipe of this kernel (the chains' and the helpers' IMAD.HI), so the epilogue
+// stays off it: byte permutes and a three-input add (PRMT, PRMT, IADD3) instead of the two IMAD the compiler makes of shift-and-add.
+__device__ __forceinline__ uint32_t shl16_alu(uint32_t v) { uint32_t r; asm("prmt.b32 %0, %1, 0, 0x1044;" : "=r"(r) : "r"(v)); return r; }
+__device__ __forceinline__ uint32_t shl8_alu(uint32_t v) { uint32_t r; asm("prmt.b32 %0, %1, 0, 0x2104;" : "=r"(r) : "r"(v)); return r; }
 __device__ __forceinline__ void drain8(uint32_t taddr, uint32_t (&acc)[8])
 {
   uint32_t a0[8], a1[8], a2[8];
@@ -112,7 +117,18 @@ __device__ __forceinline__ void drain8(uint32_t taddr, uint32_t (&acc)[8])
                : "=r"(a2[0]), "=r"(a2[1]), "=r"(a2[2]), "=r"(a2[3]), "=r"(a2[4]), "=r"(a2[5]), "=r"(a2[6]), "=r"(a2[7]) : "r"(taddr + 2u * (uint32_t)NB));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = (a0[j] << 16) + (a1[j] << 8) + a2[j];
+  for (int j = 0; j < 8; ++j) acc[j] = shl16_alu(a0[j]) + shl8_alu(a1[j]) + a2[j];
+}
+// SSB kinds on the packed words p = I | Q << 16 (Minimal-SDR.ino:591-604: the int16 sum wraps, no saturation), off the multiplier:
+//   t = p ^ xm;  upper half of t + (t << 16) + xc  = I + Q (USB: xm = xc = 0)  or  I + ~Q + 1 = I - Q (LSB: xm = 0xFFFF0000, xc = 0x10000)
+__device__ __forceinline__ void demod_ssb_alu(const uint32_t (&iq)[32], uint32_t xm, uint32_t xc, uint32_t (&out)[16])
+{
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const uint32_t u0 = iq[2 * j] ^ xm, u1 = iq[2 * j + 1] ^ xm;
+    const uint32_t t0 = u0 + shl16_alu(u0) + xc, t1 = u1 + shl16_alu(u1) + xc;
+    out[j] = __byte_perm(t0, t1, 0x7632);
+  }
 }
 // 16 window words (32 samples) of row rr -> unit `unit` of the four byte planes of one operand buffer (odd words negated: fs/4 mix,
 // Minimal-SDR.ino:550,555; a unit starts on an even word)
@@ -171,9 +187,9 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
   const uint32_t K = p.tc_K, KS = K / 32, KH = 2 * KS - 2, NSL = p.tc_ring;
   const uint32_t a_plane = a_plane6(K), b_plane = b_plane6(K);
   Ctrl *pc = reinterpret_cast<Ctrl *>(smem);
-  uint8_t *sA = smem + kCtrlBytes;            // [half][span parity][plane][unit][2][8][16]
-  uint8_t *sB = sA + 16 * a_plane;            // [plane][k unit][4 column groups][8][16]
-  unsigned char *sRaw = sB + 4 * b_plane;
+  uint8_t *sA = smem + kCtrlBytes;            // [tile number mod 3][plane][unit][2][8][16]
+  uint8_t *sB = sA + 12 * a_plane;            // [half][plane][k unit][4 column groups][8][16]
+  unsigned char *sRaw = sB + 8 * b_plane;
   unsigned char *sYb = sRaw + RS * kRawStageBytes;
   unsigned char *sSlot = sYb + 2 * kSpanBufBytes;
 
@@ -181,7 +197,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
   if (tid == 0) {
     if (p.prof) { pc->t_clk = clock64(); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(pc->t_ns)); }
     for (int i = 0; i < RS; ++i) { mbar_init(&pc->raw_full[i], 32); mbar_init(&pc->raw_free[i], 2); }
-    for (int i = 0; i < 4; ++i) { mbar_init(&pc->a_full[i], 2); mbar_init(&pc->a_free[i], 1); }
+    for (int i = 0; i < 3; ++i) { mbar_init(&pc->a_full[i], 2); mbar_init(&pc->a_free[i], 1); }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&pc->tmem_full[b], 1); mbar_init(&pc->tmem_empty[b], 4);
       mbar_init(&pc->y_full[b], 8); mbar_init(&pc->y_free[b], 1);
@@ -199,6 +215,8 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
   tc_fence_after();
   const uint32_t tmem = pc->tmem_base;
 
+  uint32_t ablate; // in a register: re-read from the constant bank once per sub-tile it cost the chains a cache miss each time
+  asm volatile("mov.u32 %0, %1;" : "=r"(ablate) : "r"(p.ablate));
   const uint32_t nspan = (p.L + SPAN - 1) / SPAN; // L is a multiple of 128: the last span may be half empty
   const uint32_t nsub = p.L / SUB;
   const uint32_t n_gb = p.n_items;
@@ -249,15 +267,15 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
     const uint32_t t = (uint32_t)(tid - kConv0 * 32), rr = t & 15u, u4 = t >> 4;
     uint32_t tseq = 0, sseq = 0, nblk = 0;
     for (uint32_t gb = blockIdx.x; gb < n_gb; gb += gridDim.x, ++nblk) {
-      { // the first 32 columns of the Toeplitz operand of this group block's table; the previous block's MMAs must be done with the old one
-        const uint32_t set = __ldg(&p.tc_rb[gb].x);
+      { // the first 32 columns of the Toeplitz operands of the two halves' tables; the previous block's MMAs must be done with the old ones
+        const uint4 rb = __ldg(&p.tc_rb[gb]);
         mbar_wait(&pc->b_free, (nblk & 1u) ^ 1u);
-        const unsigned char *src = p.tc_bmat + (size_t)set * 4u * N * K;
         const uint32_t per_plane = (K / 16u) * 32u; // 16-byte chunks
-        for (uint32_t i = t; i < 4u * per_plane; i += kConvThreads) {
-          const uint32_t pl = i / per_plane, rem = i % per_plane, ku = rem >> 5, cc = rem & 31u;
-          const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)pl * N * K + (size_t)ku * (N / 8) * 128u + cc * 16u));
-          *reinterpret_cast<uint4 *>(sB + pl * b_plane + ku * 512u + cc * 16u) = v;
+        for (uint32_t i = t; i < 8u * per_plane; i += kConvThreads) {
+          const uint32_t hp = i / per_plane, rem = i - hp * per_plane, ku = rem >> 5, cc = rem & 31u; // hp = half * 4 + plane
+          const unsigned char *src = p.tc_bmat + (size_t)(hp < 4u ? rb.x : rb.y) * 4u * N * K;
+          const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)(hp & 3u) * N * K + (size_t)ku * (N / 8) * 128u + cc * 16u));
+          *reinterpret_cast<uint4 *>(sB + hp * b_plane + ku * 512u + cc * 16u) = v;
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -267,14 +285,14 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
       for (uint32_t s = 0; s < nspan; ++s, ++sseq) {
 #pragma unroll
         for (int h = 0; h < 2; ++h, ++tseq) {
-          const uint32_t stage = tseq % RS, ab = (uint32_t)h * 2u + (sseq & 1u);
+          const uint32_t stage = tseq % RS, ab = tseq % 3u;
           const uint32_t abuf = smem_u32(sA + ab * 4u * a_plane);
           prof.start();
           mbar_wait(&pc->raw_full[stage], (tseq / RS) & 1u);
           prof.lap(0);
-          mbar_wait(&pc->a_free[ab], ((sseq >> 1) & 1u) ^ 1u);
+          mbar_wait(&pc->a_free[ab], ((tseq / 3u) & 1u) ^ 1u);
           prof.lap(1);
-          if (!(p.ablate & 1u)) {
+          if (!(ablate & 1u)) {
             const uint32_t a = smem_u32(sRaw + stage * kRawStageBytes) + rr * RAWP;
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
@@ -296,7 +314,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
                 convert_unit(abuf, a_plane, x, rr, v);
               }
             } else { // the window tail of the previous span of this half: its last KH units are this span's first
-              const uint32_t prev = smem_u32(sA + ((uint32_t)h * 2u + ((sseq & 1u) ^ 1u)) * 4u * a_plane);
+              const uint32_t prev = smem_u32(sA + ((tseq + 1u) % 3u) * 4u * a_plane); // tile tseq - 2: the same half, one span earlier
               const uint32_t per_plane = KH * (kUnitBytes / 16u);
               for (uint32_t i = t; i < 4u * per_plane; i += kConvThreads) {
                 const uint32_t pl = i / per_plane, rem = i % per_plane;
@@ -348,16 +366,16 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
       for (uint32_t s = 0; s < nspan; ++s, ++sseq) {
 #pragma unroll
         for (int h = 0; h < 2; ++h, ++tseq) {
-          const uint32_t ab = (uint32_t)h * 2u + (sseq & 1u), tb = tseq & 1u;
+          const uint32_t ab = tseq % 3u, tb = tseq & 1u;
           prof.start();
-          mbar_wait(&pc->a_full[ab], (sseq >> 1) & 1u);
+          mbar_wait(&pc->a_full[ab], (tseq / 3u) & 1u);
           prof.lap(0);
           mbar_wait(&pc->tmem_empty[tb], ((tseq >> 1) & 1u) ^ 1u);
           prof.lap(1);
           tc_fence_after();
-          if (!(p.ablate & 1u)) {
+          if (!(ablate & 1u)) {
             for (uint32_t ks = 0; ks < KS; ++ks) {
-              const uint64_t aoff = (uint64_t)((ab * 4u * a_plane + ks * 2u * kUnitBytes) >> 4), boff = (uint64_t)((ks * 2u * 512u) >> 4);
+              const uint64_t aoff = (uint64_t)((ab * 4u * a_plane + ks * 2u * kUnitBytes) >> 4), boff = (uint64_t)(((uint32_t)h * 4u * b_plane + ks * 2u * 512u) >> 4);
               const uint32_t acc = ks > 0;
 #pragma unroll
               for (uint32_t br = 0; br < 2; ++br) {
@@ -404,7 +422,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
           mbar_wait(&pc->tmem_full[tb], (tseq >> 1) & 1u);
           prof.lap(0);
           tc_fence_after();
-          if (!(p.ablate & 1u)) {
+          if (!(ablate & (1u | 8u))) {
             const uint32_t ta = lane_addr + tb * 2u * kAccCols;
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
@@ -429,7 +447,10 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
           if (lane == 0) mbar_arrive(&pc->tmem_empty[tb]);
           prof.lap(1);
           uint32_t out[16];
-          if (kind <= 1) demod_ssb_regs(iq, kind ? 0u : 0xFFFF0000u, kind ? 0u : 0x10000u, out);
+          if (ablate & 4u) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) out[j] = iq[2 * j] ^ iq[2 * j + 1];
+          } else if (kind <= 1) demod_ssb_alu(iq, kind ? 0u : 0xFFFF0000u, kind ? 0u : 0x10000u, out);
           else if (kind == 2) demod_regs<2>(iq, 0, out);
           else demod_regs<3>(iq, 0, out);
           mbar_wait(&pc->y_free[yb], ((sseq >> 1) & 1u) ^ 1u);
@@ -455,7 +476,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
     const bool is_chain = warp == kChainA || warp == kChainB;
     const int obj = (warp == kChainA || warp == kFF1) ? 0 : 1;
     Prof prof(p.prof, warp == kChainA ? 3 : warp == kChainB ? 4 : warp == kFF1 ? 7 : 8);
-    uint32_t slot = 0, phs = 0, sseq = 0; // ring position as running counters: the slot count is a run-time value, a division per sub-tile sat on the chains' path
+    uint32_t slot = 0, use = 1, sseq = 0; // ring position as running counters (slot, its use count: the mbarrier phase is its parity): the slot count is a run-time value, a division per sub-tile sat on the chains' path
     for (uint32_t gb = blockIdx.x; gb < n_gb; gb += gridDim.x) {
       const uint32_t row = __ldg(p.tc_rowmap + (size_t)gb * G + lane);
       const bool active = row != kPad;
@@ -472,12 +493,13 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
         BqRec rec{};
         uint32_t fl = 0u;
         if (fast && active) bq_load_rec(rec, fl, p.bq, p.Cpad, obj, ch);
-        for (uint32_t k = 0; k < nsub; ++k, slot = (slot + 1 == NSL ? 0 : slot + 1), phs ^= (slot == 0)) {
-          prof.start();
-          mbar_wait(isA ? &pc->ld_full[slot] : &pc->m_full[slot], phs);
+        prof.start();
+        for (uint32_t k = 0; k < nsub; ++k, slot = (slot + 1 == NSL ? 0 : slot + 1), use += (slot == 0)) {
+          prof.lap(2);
+          mbar_wait(isA ? &pc->ld_full[slot] : &pc->m_full[slot], (use & 1u) ^ 1u);
           prof.lap(0);
           const uint32_t ea = smem_u32(sSlot + slot * kSlotBytes) + (uint32_t)lane * (EW * 4u), ya = smem_u32(sSlot + slot * kSlotBytes) + (uint32_t)(G * EW * 4) + (uint32_t)lane * (YW * 4u);
-          if (!(p.ablate & 2u) && active) {
+          if (!(ablate & 2u) && active) {
             if (fast) {
               uint4 n0 = lds128(ea), n1 = lds128(ea + 16u);
 #pragma unroll 1
@@ -518,6 +540,8 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
         const bool isF1 = warp == kFF1;
         FFT ff{};
         if (fast && active) bq_load_ff(ff, p.bq, p.Cpad, obj, ch);
+        bool sym = false;
+        if constexpr (sizeof(FFT) == sizeof(BqFFI)) sym = __all_sync(0xffffffffu, !(fast && active) || ff.b0 == ff.b2) && !(ablate & 16u);
         for (uint32_t s = 0; s < nspan; ++s, ++sseq) {
           const uint32_t yb = sseq & 1u;
           if (isF1) {
@@ -526,20 +550,48 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
             prof.lap(3);
           }
           const uint32_t nk = min(4u, nsub - 4u * s);
-          for (uint32_t k = 0; k < nk; ++k, slot = (slot + 1 == NSL ? 0 : slot + 1), phs ^= (slot == 0)) {
+          for (uint32_t k = 0; k < nk; ++k, slot = (slot + 1 == NSL ? 0 : slot + 1), use += (slot == 0)) {
             const uint32_t ea = smem_u32(sSlot + slot * kSlotBytes) + (uint32_t)lane * (EW * 4u), ya = smem_u32(sSlot + slot * kSlotBytes) + (uint32_t)(G * EW * 4) + (uint32_t)lane * (YW * 4u);
             prof.start();
             uint32_t src;
             if (isF1) {
-              mbar_wait(&pc->slot_free[slot], phs ^ 1u);
+              mbar_wait(&pc->slot_free[slot], use & 1u);
               src = smem_u32(sYb + yb * kSpanBufBytes) + (uint32_t)lane * RAWP + k * (SUB * 2u);
             } else {
-              mbar_wait(&pc->ab_full[slot], phs);
+              mbar_wait(&pc->ab_full[slot], (use & 1u) ^ 1u);
               src = ya;
             }
             prof.lap(0);
             uint4 nx = lds128(src);
-            if (active && fast) { // branch-free straight-line code: the samples are independent, their products overlap
+            if (active && fast && sym) {
+              // symmetric numerator (b0 == b2, every low-pass / notch section): hi(b2 x[n-2]) is the product hi(b0 x[n-2]) formed two
+              // samples ago - two multiplies per sample instead of three
+              if constexpr (sizeof(FFT) == sizeof(BqFFI)) {
+                int q1, r1, r2;
+                asm("mul.hi.s32 %0, %1, %2;" : "=r"(q1) : "r"(ff.b1), "r"(ff.x1));
+                asm("mul.hi.s32 %0, %1, %2;" : "=r"(r1) : "r"(ff.b0), "r"(ff.x1));
+                asm("mul.hi.s32 %0, %1, %2;" : "=r"(r2) : "r"(ff.b0), "r"(ff.x2));
+#pragma unroll
+                for (int j = 0; j < SUB / 8; ++j) {
+                  const uint32_t w[4] = {nx.x, nx.y, nx.z, nx.w};
+                  if (j + 1 < SUB / 8) nx = lds128(src + 16u * (uint32_t)(j + 1));
+                  uint32_t e[8];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    const int xs = (i & 1) ? (int)(w[i >> 1] & 0xFFFF0000u) : (int)(w[i >> 1] << 16);
+                    int p0;
+                    asm("mul.hi.s32 %0, %1, %2;" : "=r"(p0) : "r"(ff.b0), "r"(xs));
+                    e[i] = (uint32_t)(p0 + q1 + r2);
+                    r2 = r1; r1 = p0;
+                    asm("mul.hi.s32 %0, %1, %2;" : "=r"(q1) : "r"(ff.b1), "r"(xs));
+                    if (j == SUB / 8 - 1 && i == 6) ff.x2 = xs;
+                    if (j == SUB / 8 - 1 && i == 7) ff.x1 = xs;
+                  }
+                  sts128(ea + 32u * (uint32_t)j, make_uint4(e[0], e[1], e[2], e[3]));
+                  sts128(ea + 32u * (uint32_t)j + 16u, make_uint4(e[4], e[5], e[6], e[7]));
+                }
+              }
+            } else if (active && fast) { // branch-free straight-line code: the samples are independent, their products overlap
 #pragma unroll
               for (int j = 0; j < SUB / 8; ++j) {
                 const uint32_t w[4] = {nx.x, nx.y, nx.z, nx.w};
@@ -585,15 +637,15 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
     Prof prof(p.prof, 6);
     const int r0 = lane >> 3, c = lane & 7;
     uint4 *out16 = reinterpret_cast<uint4 *>(p.out);
-    uint32_t slot = 0, phs = 0;
+    uint32_t slot = 0, use = 1;
     for (uint32_t gb = blockIdx.x; gb < n_gb; gb += gridDim.x) {
       const uint32_t *rmap = p.tc_rowmap + (size_t)gb * G;
       uint32_t rows[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) rows[i] = __ldg(rmap + r0 + 4 * i);
-      for (uint32_t k = 0; k < nsub; ++k, slot = (slot + 1 == NSL ? 0 : slot + 1), phs ^= (slot == 0)) {
+      for (uint32_t k = 0; k < nsub; ++k, slot = (slot + 1 == NSL ? 0 : slot + 1), use += (slot == 0)) {
         prof.start();
-        mbar_wait(&pc->st_full[slot], phs);
+        mbar_wait(&pc->st_full[slot], (use & 1u) ^ 1u);
         prof.lap(0);
         const uint32_t sa = smem_u32(sSlot + slot * kSlotBytes) + (uint32_t)(G * EW * 4) + (uint32_t)r0 * (YW * 4u) + (uint32_t)c * 16u;
         const uint32_t col16 = k * (SUB / 8) + (uint32_t)c;
@@ -629,6 +681,7 @@ cudaError_t launch_chain_v6(const ChainParams &p_in, cudaStream_t stream, int va
   using namespace v6;
   ChainParams p = p_in;
   p.ablate = ((uint32_t)variant >> 4) & 3u;
+  if (const char *ev = getenv("MSDR_ABLATE")) p.ablate |= (uint32_t)atoi(ev) & ~3u; // study only: 4 = no demodulation, 8 = no TMEM drain (results are wrong)
   const size_t smem = smem_bytes(p.tc_K, p.tc_ring);
   auto kern = (variant & 2) ? chain_kernel<BqFF> : chain_kernel<BqFFI>; // study knob: bit 1 = feed-forward products as DFMA
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for v in 0; do
-MSDR_PROF=1 timeout 600 python bench.py --variant $v --steps 1 --warmup 1 --no-cpu --no-parity --e2e-steps 0 --seconds 2.97 > gpurun_out/abl_$v.txt 2>&1
-echo "== variant $v"; grep -A10 "prof v6" gpurun_out/abl_$v.txt | tail -10 | cut -c1-158
+for sec in 2.97; do
+MSDR_PROF=1 timeout 600 python bench.py --steps 1 --warmup 1 --no-cpu --no-parity --e2e-steps 0 --seconds $sec > gpurun_out/len_$sec.txt 2>&1
+echo "== seconds $sec"; grep -A10 "prof v6" gpurun_out/len_$sec.txt | tail -10 | cut -c1-60 | sed -n '4,5p;10p'
 done
