@@ -935,11 +935,11 @@ int msdr_chain_update_range_device(msdr_chain *chain, uint32_t ch0, uint32_t nch
     st = build_tc_plan(chain, ch0, nch, (uint32_t)sms, want_dual, &plp);
     if (st != MSDR_OK) return st;
     const msdr_chain::TcPlan &pl = *plp;
-    // Few channels: the time-folded kernel (msdr_chain_v6.cu), one CTA per 32 same-table channels, nothing leaves the SM.  Up to two
-    // group blocks per SM; beyond that the two chain sets per SM of msdr_chain_v4.cu (and then the row-block kernel) are faster.
-    // variant bit 16 forces it for any channel count (parity tests), bit 14 forbids it.
+    // Few channels: the time-folded kernel (msdr_chain_v6.cu), one CTA per 32 same-table channels, nothing leaves the SM.  One group
+    // block per SM: a second round would double the launch, and beyond that the two chain sets per SM of msdr_chain_v4.cu (then the
+    // row-block kernel) are faster.  variant bit 16 forces it for any channel count (parity tests), bit 14 forbids it.
     const bool use_v6 = pl.usable && pl.slots_v6 && !(chain->variant & (16384 | 128 | 256 | 512 | 2048)) &&
-                        ((chain->variant & 65536) || pl.n_gb <= 2u * (uint32_t)sms);
+                        ((chain->variant & 65536) || pl.n_gb <= (uint32_t)std::max(1, sms - (int)chain->spare_sms));
     if (use_v6) {
       p.NG = NG;
       p.n_items = pl.n_gb;
