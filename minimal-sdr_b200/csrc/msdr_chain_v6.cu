@@ -117,7 +117,11 @@ __device__ __forceinline__ void drain8(uint32_t taddr, uint32_t (&acc)[8])
                : "=r"(a2[0]), "=r"(a2[1]), "=r"(a2[2]), "=r"(a2[3]), "=r"(a2[4]), "=r"(a2[5]), "=r"(a2[6]), "=r"(a2[7]) : "r"(taddr + 2u * (uint32_t)NB));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
+#ifdef MSDR_V6_EPI_IMAD
+  for (int j = 0; j < 8; ++j) acc[j] = (a0[j] << 16) + (a1[j] << 8) + a2[j];
+#else
   for (int j = 0; j < 8; ++j) acc[j] = shl16_alu(a0[j]) + shl8_alu(a1[j]) + a2[j];
+#endif
 }
 // SSB kinds on the packed words p = I | Q << 16 (Minimal-SDR.ino:591-604: the int16 sum wraps, no saturation), off the multiplier:
 //   t = p ^ xm;  upper half of t + (t << 16) + xc  = I + Q (USB: xm = xc = 0)  or  I + ~Q + 1 = I - Q (LSB: xm = 0xFFFF0000, xc = 0x10000)
@@ -450,7 +454,12 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
           if (ablate & 4u) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) out[j] = iq[2 * j] ^ iq[2 * j + 1];
-          } else if (kind <= 1) demod_ssb_alu(iq, kind ? 0u : 0xFFFF0000u, kind ? 0u : 0x10000u, out);
+          }
+#ifdef MSDR_V6_EPI_IMAD
+          else if (kind <= 1) demod_ssb_regs(iq, kind ? 0u : 0xFFFF0000u, kind ? 0u : 0x10000u, out);
+#else
+          else if (kind <= 1) demod_ssb_alu(iq, kind ? 0u : 0xFFFF0000u, kind ? 0u : 0x10000u, out);
+#endif
           else if (kind == 2) demod_regs<2>(iq, 0, out);
           else demod_regs<3>(iq, 0, out);
           mbar_wait(&pc->y_free[yb], ((sseq >> 1) & 1u) ^ 1u);
