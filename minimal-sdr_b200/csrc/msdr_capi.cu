@@ -995,8 +995,9 @@ int msdr_chain_update_range_device(msdr_chain *chain, uint32_t ch0, uint32_t nch
         }
         if (getenv("MSDR_PROF_CTAS")) // per-CTA totals of chain A (wait, work) and the epilogue
           for (uint32_t b = 0; b < g; ++b)
-            fprintf(stderr, "  cta %3u chainA %9lld %9lld  epilogue %9lld %9lld %9lld %9lld\n", b, h[(size_t)b * 64 + 12], h[(size_t)b * 64 + 13], h[(size_t)b * 64 + 8],
-                    h[(size_t)b * 64 + 9], h[(size_t)b * 64 + 10], h[(size_t)b * 64 + 11]);
+            fprintf(stderr, "  cta %3u sm %3lld start %8lld ns total %9lld cyc  chainA %9lld %9lld %9lld  ff1 %9lld %9lld yfull %9lld  epilogue %9lld %9lld %9lld %9lld\n", b,
+                    h[(size_t)b * 64 + 42], h[(size_t)b * 64 + 43] - h[43], h[(size_t)b * 64 + 40], h[(size_t)b * 64 + 12], h[(size_t)b * 64 + 13], h[(size_t)b * 64 + 14],
+                    h[(size_t)b * 64 + 28], h[(size_t)b * 64 + 29], h[(size_t)b * 64 + 31], h[(size_t)b * 64 + 8], h[(size_t)b * 64 + 9], h[(size_t)b * 64 + 10], h[(size_t)b * 64 + 11]);
       }
       return MSDR_OK;
     }

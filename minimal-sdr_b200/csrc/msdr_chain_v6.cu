@@ -64,6 +64,7 @@ constexpr uint32_t kSpanBufBytes = G * RAWP;
 constexpr uint32_t kUnitBytes = 2 * 128;                      // one unit (16 window words) of one plane: 2 channel groups x 128 B
 constexpr uint32_t kAccCols = 3 * NB;                         // TMEM columns of one branch of a tile
 constexpr uint32_t kCtrlBytes = 1024;
+constexpr uint32_t kScratchBytes = 4 * 2048;                 // epilogue: one demodulated tile part per warp, [column group][lane][16 B]
 struct __align__(16) Ctrl {
   uint64_t raw_full[RS];          // load -> convert   : the stage's copies have landed (32 arrivals, cp.async.mbarrier.arrive.noinc)
   uint64_t raw_free[RS];          // convert -> load   : stage read (2 arrivals)
@@ -89,7 +90,7 @@ __host__ __device__ inline uint32_t a_plane6(uint32_t K) { return units_per_buf(
 __host__ __device__ inline uint32_t b_plane6(uint32_t K) { return (uint32_t)NB * K; }
 size_t smem_bytes(uint32_t K, uint32_t nslot)
 {
-  return (size_t)kCtrlBytes + 12u * a_plane6(K) + 8u * b_plane6(K) + (size_t)RS * kRawStageBytes + 2u * kSpanBufBytes + (size_t)nslot * kSlotBytes + 1024u;
+  return (size_t)kCtrlBytes + 12u * a_plane6(K) + 8u * b_plane6(K) + (size_t)RS * kRawStageBytes + 2u * kSpanBufBytes + kScratchBytes + (size_t)nslot * kSlotBytes + 1024u;
 }
 
 __device__ __forceinline__ void umma_i8_n32(uint32_t dcol, uint64_t da, uint64_t db, uint32_t a_signed, uint32_t b_signed, uint32_t acc)
@@ -195,7 +196,8 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
   uint8_t *sB = sA + 12 * a_plane;            // [half][plane][k unit][4 column groups][8][16]
   unsigned char *sRaw = sB + 8 * b_plane;
   unsigned char *sYb = sRaw + RS * kRawStageBytes;
-  unsigned char *sSlot = sYb + 2 * kSpanBufBytes;
+  unsigned char *sScr = sYb + 2 * kSpanBufBytes;
+  unsigned char *sSlot = sScr + kScratchBytes;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
@@ -416,57 +418,66 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
         const uint32_t row = __ldg(p.tc_rowmap + (size_t)gb * G + h * HR + rr);
         kind2[h] = row != kPad ? demod_kind_of((int)p.mode[p.ch0 + row], p.am_q31) : 0;
       }
+      // The loops below are deliberately NOT unrolled over tiles and column groups: the kernel's roles together stream far more
+      // straight-line code than the instruction caches hold, and SMs with a longer path to the next cache level fell 7 % behind
+      // (deterministic per SM).  Eight columns per pass through a 2 KB scratch part of this warp keep the epilogue's hot code small.
+      const uint32_t scr = smem_u32(sScr) + (uint32_t)warp * 2048u + (uint32_t)lane * 16u;
       for (uint32_t s = 0; s < nspan; ++s, ++sseq) {
-#pragma unroll
+#pragma unroll 1
         for (int h = 0; h < 2; ++h, ++tseq) {
           const uint32_t tb = tseq & 1u, yb = sseq & 1u;
-          const int kind = kind2[h];
-          uint32_t iq[32];
+          const int kind = h ? kind2[1] : kind2[0];
           prof.start();
           mbar_wait(&pc->tmem_full[tb], (tseq >> 1) & 1u);
           prof.lap(0);
           tc_fence_after();
-          if (!(ablate & (1u | 8u))) {
-            const uint32_t ta = lane_addr + tb * 2u * kAccCols;
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-              uint32_t ai[8];
+          const uint32_t ta = lane_addr + tb * 2u * kAccCols;
+#pragma unroll 1
+          for (int b = 0; b < 4; ++b) {
+            uint32_t iq[8], o[4];
+            if (!(ablate & (1u | 8u))) {
+              uint32_t ai[8], aq[8];
               drain8(ta + (uint32_t)(8 * b), ai);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) iq[8 * b + j] = (uint32_t)((int)ai[j] >> 15); // saturated together with Q below
-            }
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-              uint32_t aq[8];
               drain8(ta + kAccCols + (uint32_t)(8 * b), aq);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) iq[8 * b + j] = pack_sat_iq((int)iq[8 * b + j], (int)aq[j] >> 15);
-            }
-          } else {
+              for (int j = 0; j < 8; ++j) iq[j] = pack_sat_iq((int)ai[j] >> 15, (int)aq[j] >> 15);
+            } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) iq[j] = 0u;
+              for (int j = 0; j < 8; ++j) iq[j] = 0u;
+            }
+            if (ablate & 4u) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) o[j] = iq[2 * j] ^ iq[2 * j + 1];
+            } else if (kind <= 1) { // SSB kinds on the packed words p = I | Q << 16 (demod_ssb_alu)
+              const uint32_t xm = kind ? 0u : 0xFFFF0000u, xc = kind ? 0u : 0x10000u;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint32_t u0 = iq[2 * j] ^ xm, u1 = iq[2 * j + 1] ^ xm;
+                o[j] = __byte_perm(u0 + shl16_alu(u0) + xc, u1 + shl16_alu(u1) + xc, 0x7632);
+              }
+            } else { // envelope kinds: eight square roots in flight
+              int y[8];
+              if (kind == 2) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) y[j] = demod_inline<2>((int)(short)(iq[j] & 0xFFFFu), (int)iq[j] >> 16, 0);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) y[j] = demod_inline<3>((int)(short)(iq[j] & 0xFFFFu), (int)iq[j] >> 16, 0);
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) o[j] = ((uint32_t)y[2 * j] & 0xFFFFu) | ((uint32_t)y[2 * j + 1] << 16);
+            }
+            sts128(scr + (uint32_t)b * 512u, make_uint4(o[0], o[1], o[2], o[3]));
           }
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&pc->tmem_empty[tb]);
           prof.lap(1);
-          uint32_t out[16];
-          if (ablate & 4u) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) out[j] = iq[2 * j] ^ iq[2 * j + 1];
-          }
-#ifdef MSDR_V6_EPI_IMAD
-          else if (kind <= 1) demod_ssb_regs(iq, kind ? 0u : 0xFFFF0000u, kind ? 0u : 0x10000u, out);
-#else
-          else if (kind <= 1) demod_ssb_alu(iq, kind ? 0u : 0xFFFF0000u, kind ? 0u : 0x10000u, out);
-#endif
-          else if (kind == 2) demod_regs<2>(iq, 0, out);
-          else demod_regs<3>(iq, 0, out);
           mbar_wait(&pc->y_free[yb], ((sseq >> 1) & 1u) ^ 1u);
           prof.lap(2);
           const uint32_t ya = smem_u32(sYb + yb * kSpanBufBytes) + ((uint32_t)h * HR + rr) * RAWP + q * 64u;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) sts128(ya + 16u * j, make_uint4(out[4 * j], out[4 * j + 1], out[4 * j + 2], out[4 * j + 3]));
+          for (int j = 0; j < 4; ++j) sts128(ya + 16u * j, lds128(scr + (uint32_t)j * 512u)); // this thread's own words
           __syncwarp();
           if (lane == 0) mbar_arrive(&pc->y_full[yb]);
           prof.lap(3);
@@ -543,6 +554,9 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
           asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
           long long *b = p.prof + (size_t)blockIdx.x * 64 + 40;
           b[0] = clock64() - pc->t_clk; b[1] = ns - pc->t_ns;
+          uint32_t smid;
+          asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+          b[2] = (long long)smid; b[3] = pc->t_ns;
         }
       } else {
         // feed-forward helpers.  FF1: span buffer -> e1 (object 1);  FF2: y1 (Y rows of the slot) -> e2 (object 2)
@@ -572,15 +586,16 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
             }
             prof.lap(0);
             uint4 nx = lds128(src);
+            // (loops over the eight-sample groups are not unrolled: see the epilogue's note on instruction-cache footprint)
             if (active && fast && sym) {
               // symmetric numerator (b0 == b2, every low-pass / notch section): hi(b2 x[n-2]) is the product hi(b0 x[n-2]) formed two
               // samples ago - two multiplies per sample instead of three
               if constexpr (sizeof(FFT) == sizeof(BqFFI)) {
-                int q1, r1, r2;
-                asm("mul.hi.s32 %0, %1, %2;" : "=r"(q1) : "r"(ff.b1), "r"(ff.x1));
-                asm("mul.hi.s32 %0, %1, %2;" : "=r"(r1) : "r"(ff.b0), "r"(ff.x1));
-                asm("mul.hi.s32 %0, %1, %2;" : "=r"(r2) : "r"(ff.b0), "r"(ff.x2));
-#pragma unroll
+                int q1, r1, r2, x1 = ff.x1, x2 = ff.x2;
+                asm("mul.hi.s32 %0, %1, %2;" : "=r"(q1) : "r"(ff.b1), "r"(x1));
+                asm("mul.hi.s32 %0, %1, %2;" : "=r"(r1) : "r"(ff.b0), "r"(x1));
+                asm("mul.hi.s32 %0, %1, %2;" : "=r"(r2) : "r"(ff.b0), "r"(x2));
+#pragma unroll 1
                 for (int j = 0; j < SUB / 8; ++j) {
                   const uint32_t w[4] = {nx.x, nx.y, nx.z, nx.w};
                   if (j + 1 < SUB / 8) nx = lds128(src + 16u * (uint32_t)(j + 1));
@@ -593,15 +608,15 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
                     e[i] = (uint32_t)(p0 + q1 + r2);
                     r2 = r1; r1 = p0;
                     asm("mul.hi.s32 %0, %1, %2;" : "=r"(q1) : "r"(ff.b1), "r"(xs));
-                    if (j == SUB / 8 - 1 && i == 6) ff.x2 = xs;
-                    if (j == SUB / 8 - 1 && i == 7) ff.x1 = xs;
                   }
+                  x2 = (int)(w[3] << 16); x1 = (int)(w[3] & 0xFFFF0000u);
                   sts128(ea + 32u * (uint32_t)j, make_uint4(e[0], e[1], e[2], e[3]));
                   sts128(ea + 32u * (uint32_t)j + 16u, make_uint4(e[4], e[5], e[6], e[7]));
                 }
+                ff.x1 = x1; ff.x2 = x2;
               }
-            } else if (active && fast) { // branch-free straight-line code: the samples are independent, their products overlap
-#pragma unroll
+            } else if (active && fast) {
+#pragma unroll 1
               for (int j = 0; j < SUB / 8; ++j) {
                 const uint32_t w[4] = {nx.x, nx.y, nx.z, nx.w};
                 if (j + 1 < SUB / 8) nx = lds128(src + 16u * (uint32_t)(j + 1));
@@ -620,7 +635,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
                 sts128(ea + 32u * (uint32_t)j + 16u, make_uint4(e[4], e[5], e[6], e[7]));
               }
             } else if (active) { // generic cascade: hand x << 16 through
-#pragma unroll
+#pragma unroll 1
               for (int j = 0; j < SUB / 8; ++j) {
                 const uint32_t w[4] = {nx.x, nx.y, nx.z, nx.w};
                 if (j + 1 < SUB / 8) nx = lds128(src + 16u * (uint32_t)(j + 1));
