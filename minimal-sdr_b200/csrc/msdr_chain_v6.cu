@@ -155,9 +155,9 @@ __device__ __forceinline__ void convert_unit(uint32_t abuf, uint32_t a_plane, ui
   sts128(off + 3 * a_plane, make_uint4(ol[0], ol[1], ol[2], ol[3]));
 }
 
-// The three input-side products of a stage (msdr_chain_common.cuh: BqFF) as IMAD.HI on values carried as x << 16.  The DFMA form of
-// the chain kernel keeps the integer multiplier of a crowded sub-partition free; here the helpers' sub-partitions are nearly idle, and
-// the fixed-latency integer pipe needs no scoreboard per product group (one warp: 17 instead of 36 cycles per sample).
+// The three input-side products of a stage (msdr_chain_common.cuh: BqFF) as IMAD.HI on values carried as x << 16: the study form
+// (variant bit 1).  The default keeps them on the FP64 pipe (exact DFMA.RM), which leaves the integer multiplier of the helpers'
+// sub-partitions to nobody in particular but measures 1 % faster (3.4M against 4.1M cycles per launch in the helper warps).
 struct BqFFI {
   int b0, b1, b2;
   int x1, x2; // << 16
@@ -564,7 +564,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
         FFT ff{};
         if (fast && active) bq_load_ff(ff, p.bq, p.Cpad, obj, ch);
         bool sym = false;
-        if constexpr (sizeof(FFT) == sizeof(BqFFI)) sym = __all_sync(0xffffffffu, !(fast && active) || ff.b0 == ff.b2) && !(ablate & 16u);
+        sym = __all_sync(0xffffffffu, !(fast && active) || ff.b0 == ff.b2) && !(ablate & 16u);
         for (uint32_t s = 0; s < nspan; ++s, ++sseq) {
           const uint32_t yb = sseq & 1u;
           if (isF1) {
@@ -610,6 +610,28 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
                     asm("mul.hi.s32 %0, %1, %2;" : "=r"(q1) : "r"(ff.b1), "r"(xs));
                   }
                   x2 = (int)(w[3] << 16); x1 = (int)(w[3] & 0xFFFF0000u);
+                  sts128(ea + 32u * (uint32_t)j, make_uint4(e[0], e[1], e[2], e[3]));
+                  sts128(ea + 32u * (uint32_t)j + 16u, make_uint4(e[4], e[5], e[6], e[7]));
+                }
+                ff.x1 = x1; ff.x2 = x2;
+              } else { // the same with the products as exact DFMA.RM (msdr_chain_common.cuh: BqFF)
+                int q1 = __double2loint(__fma_rd(ff.b1, ff.x1, ff.m1)), r1 = __double2loint(__fma_rd(ff.b0, ff.x1, ff.m0)), r2 = __double2loint(__fma_rd(ff.b0, ff.x2, ff.m0));
+                double x1 = ff.x1, x2 = ff.x2;
+#pragma unroll 1
+                for (int j = 0; j < SUB / 8; ++j) {
+                  const uint32_t w[4] = {nx.x, nx.y, nx.z, nx.w};
+                  if (j + 1 < SUB / 8) nx = lds128(src + 16u * (uint32_t)(j + 1));
+                  uint32_t e[8];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    const double xD = bq_d_from_int((i & 1) ? (int)w[i >> 1] >> 16 : (int)(short)(w[i >> 1] & 0xFFFFu));
+                    const int p0 = __double2loint(__fma_rd(ff.b0, xD, ff.m0));
+                    e[i] = (uint32_t)(p0 + q1 + r2);
+                    r2 = r1; r1 = p0;
+                    q1 = __double2loint(__fma_rd(ff.b1, xD, ff.m1));
+                    if (i == 6) x2 = xD;
+                    if (i == 7) x1 = xD;
+                  }
                   sts128(ea + 32u * (uint32_t)j, make_uint4(e[0], e[1], e[2], e[3]));
                   sts128(ea + 32u * (uint32_t)j + 16u, make_uint4(e[4], e[5], e[6], e[7]));
                 }
@@ -707,7 +729,7 @@ cudaError_t launch_chain_v6(const ChainParams &p_in, cudaStream_t stream, int va
   p.ablate = ((uint32_t)variant >> 4) & 3u;
   if (const char *ev = getenv("MSDR_ABLATE")) p.ablate |= (uint32_t)atoi(ev) & ~3u; // study only: 4 = no demodulation, 8 = no TMEM drain (results are wrong)
   const size_t smem = smem_bytes(p.tc_K, p.tc_ring);
-  auto kern = (variant & 2) ? chain_kernel<BqFF> : chain_kernel<BqFFI>; // study knob: bit 1 = feed-forward products as DFMA
+  auto kern = (variant & 2) ? chain_kernel<BqFFI> : chain_kernel<BqFF>; // study knob: bit 1 = feed-forward products as IMAD.HI instead of DFMA
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const uint32_t grid = p.n_items < (uint32_t)sms ? p.n_items : (uint32_t)sms;
