@@ -55,9 +55,9 @@ constexpr int QB = 8;             // time blocks of a tile
 constexpr int SPAN = QB * NB;     // samples of a tile row set = 256
 constexpr int SUB = 64;           // chain sub-tile, samples
 constexpr int RS = 2;             // raw staging stages
-constexpr int NSLOT_MAX = 8;
-constexpr int EW = SUB + 4, YW = SUB / 2 + 4;                 // sub-tile slot: e[n] rows (32-bit) and packed int16 rows, word pitches
-constexpr uint32_t kSlotBytes = G * (EW + YW) * 4u;           // 13312
+constexpr int NSLOT_MAX = 12;      // both rings together (p.tc_ring, even); the barrier arrays are indexed per ring
+constexpr int EW = SUB + 4;                                   // sub-tile slot: rows of 64 e[n] words; the packed int16 results overwrite the row's front
+constexpr uint32_t kSlotBytes = G * EW * 4u;                  // 8704
 constexpr uint32_t RAWP = SPAN * 2 + 16;                      // staging / span buffer row pitch in bytes (16 mod 128: conflict-free)
 constexpr uint32_t kRawStageBytes = HR * RAWP;
 constexpr uint32_t kSpanBufBytes = G * RAWP;
@@ -75,11 +75,13 @@ struct __align__(16) Ctrl {
   uint64_t b_full, b_free;        // convert <-> MMA   : Toeplitz operand of the group block's table
   uint64_t y_full[2];             // epilogue -> FF1   : span buffer complete (8 arrivals: 4 warps x 2 tiles)
   uint64_t y_free[2];             // FF1 -> epilogue
+  // two rings of sub-tile slots: ring 1 FF1 -> chain A -> FF2, ring 2 FF2 -> chain B -> store (indices are per ring)
   uint64_t ld_full[NSLOT_MAX];    // FF1 -> chain A
   uint64_t ab_full[NSLOT_MAX];    // chain A -> FF2
   uint64_t m_full[NSLOT_MAX];     // FF2 -> chain B
   uint64_t st_full[NSLOT_MAX];    // chain B -> store
-  uint64_t slot_free[NSLOT_MAX];  // store -> FF1
+  uint64_t slot_free[NSLOT_MAX];  // FF2 -> FF1        : ring 1 slot read
+  uint64_t free2[NSLOT_MAX];      // store -> FF2      : ring 2 slot stored
   uint32_t tmem_base;
   long long t_clk, t_ns; // developer profile: kernel entry
 };
@@ -155,9 +157,10 @@ __device__ __forceinline__ void convert_unit(uint32_t abuf, uint32_t a_plane, ui
   sts128(off + 3 * a_plane, make_uint4(ol[0], ol[1], ol[2], ol[3]));
 }
 
-// The three input-side products of a stage (msdr_chain_common.cuh: BqFF) as IMAD.HI on values carried as x << 16: the study form
-// (variant bit 1).  The default keeps them on the FP64 pipe (exact DFMA.RM), which leaves the integer multiplier of the helpers'
-// sub-partitions to nobody in particular but measures 1 % faster (3.4M against 4.1M cycles per launch in the helper warps).
+// The three input-side products of a stage (msdr_chain_common.cuh: BqFF) as IMAD.HI on values carried as x << 16.  The chain kernel
+// keeps them on the FP64 pipe (exact DFMA.RM) because its helpers share a crowded sub-partition; here the helpers' sub-partitions
+// have the integer multiplier nearly to themselves and the fixed-latency pipe needs no scoreboard per product group: 196 against
+// 188 Gsamples/s at C3 (variant bit 1 selects the DFMA form).
 struct BqFFI {
   int b0, b1, b2;
   int x1, x2; // << 16
@@ -189,7 +192,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
 {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023u) & ~(uintptr_t)1023u);
-  const uint32_t K = p.tc_K, KS = K / 32, KH = 2 * KS - 2, NSL = p.tc_ring;
+  const uint32_t K = p.tc_K, KS = K / 32, KH = 2 * KS - 2, NH = p.tc_ring / 2; // slots per ring
   const uint32_t a_plane = a_plane6(K), b_plane = b_plane6(K);
   Ctrl *pc = reinterpret_cast<Ctrl *>(smem);
   uint8_t *sA = smem + kCtrlBytes;            // [tile number mod 3][plane][unit][2][8][16]
@@ -211,7 +214,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
     mbar_init(&pc->b_full, 2);
     mbar_init(&pc->b_free, 1);
     for (int s = 0; s < NSLOT_MAX; ++s) {
-      mbar_init(&pc->ld_full[s], 1); mbar_init(&pc->ab_full[s], 1); mbar_init(&pc->m_full[s], 1); mbar_init(&pc->st_full[s], 1); mbar_init(&pc->slot_free[s], 1);
+      mbar_init(&pc->ld_full[s], 1); mbar_init(&pc->ab_full[s], 1); mbar_init(&pc->m_full[s], 1); mbar_init(&pc->st_full[s], 1); mbar_init(&pc->slot_free[s], 1); mbar_init(&pc->free2[s], 1);
     }
     mbar_fence_init();
   }
@@ -492,7 +495,8 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
     }
   } else if (warp == kChainA || warp == kChainB || warp == kFF1 || warp == kFF2) {
     // ================================================================== chain side: lane = channel of the group block
-    // slot = E rows [32][EW] (32-bit: feed-forward sums, or x << 16 for generic cascades) + Y rows [32][YW] (packed int16)
+    // slot = rows [32][EW] of 32-bit words: feed-forward sums (or x << 16 for generic cascades), overwritten in place by the stage's packed
+    // int16 results (front 128 bytes of the row)
     const bool is_chain = warp == kChainA || warp == kChainB;
     const int obj = (warp == kChainA || warp == kFF1) ? 0 : 1;
     Prof prof(p.prof, warp == kChainA ? 3 : warp == kChainB ? 4 : warp == kFF1 ? 7 : 8);
@@ -514,11 +518,12 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
         uint32_t fl = 0u;
         if (fast && active) bq_load_rec(rec, fl, p.bq, p.Cpad, obj, ch);
         prof.start();
-        for (uint32_t k = 0; k < nsub; ++k, slot = (slot + 1 == NSL ? 0 : slot + 1), use += (slot == 0)) {
+        for (uint32_t k = 0; k < nsub; ++k, slot = (slot + 1 == NH ? 0 : slot + 1), use += (slot == 0)) {
           prof.lap(2);
           mbar_wait(isA ? &pc->ld_full[slot] : &pc->m_full[slot], (use & 1u) ^ 1u);
           prof.lap(0);
-          const uint32_t ea = smem_u32(sSlot + slot * kSlotBytes) + (uint32_t)lane * (EW * 4u), ya = smem_u32(sSlot + slot * kSlotBytes) + (uint32_t)(G * EW * 4) + (uint32_t)lane * (YW * 4u);
+          // in place: the eight results of a pass (16 bytes) go where the row's e[n] words have already been read (32 bytes per pass)
+          const uint32_t ea = smem_u32(sSlot + (isA ? slot : NH + slot) * kSlotBytes) + (uint32_t)lane * (EW * 4u), ya = ea;
           if (!(ablate & 2u) && active) {
             if (fast) {
               uint4 n0 = lds128(ea), n1 = lds128(ea + 16u);
@@ -532,8 +537,8 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
                                                            __byte_perm((uint32_t)y4, (uint32_t)y5, 0x7632), __byte_perm((uint32_t)y6, (uint32_t)y7, 0x7632)));
               }
             } else { // generic cascade, stage-major like the reference (filter_biquad.cpp:44-79): E holds x << 16, filtered in place
-              uint32_t *er = reinterpret_cast<uint32_t *>(sSlot + slot * kSlotBytes) + (uint32_t)lane * EW;
-              uint32_t *yr = reinterpret_cast<uint32_t *>(sSlot + slot * kSlotBytes) + G * EW + (uint32_t)lane * YW;
+              uint32_t *er = reinterpret_cast<uint32_t *>(sSlot + (isA ? slot : NH + slot) * kSlotBytes) + (uint32_t)lane * EW;
+              uint32_t *yr = er; // packed in place, word n after words 2 n and 2 n + 1 were read
               for (int j = 0; j < nst; ++j) {
                 BqStage gs;
                 uint32_t gf;
@@ -573,8 +578,9 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
             prof.lap(3);
           }
           const uint32_t nk = min(4u, nsub - 4u * s);
-          for (uint32_t k = 0; k < nk; ++k, slot = (slot + 1 == NSL ? 0 : slot + 1), use += (slot == 0)) {
-            const uint32_t ea = smem_u32(sSlot + slot * kSlotBytes) + (uint32_t)lane * (EW * 4u), ya = smem_u32(sSlot + slot * kSlotBytes) + (uint32_t)(G * EW * 4) + (uint32_t)lane * (YW * 4u);
+          for (uint32_t k = 0; k < nk; ++k, slot = (slot + 1 == NH ? 0 : slot + 1), use += (slot == 0)) {
+            // FF1 fills a slot of ring 1; FF2 reads chain A's results from that slot's rows (their front halves) and fills a slot of ring 2
+            const uint32_t ea = smem_u32(sSlot + (isF1 ? slot : NH + slot) * kSlotBytes) + (uint32_t)lane * (EW * 4u);
             prof.start();
             uint32_t src;
             if (isF1) {
@@ -582,7 +588,8 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
               src = smem_u32(sYb + yb * kSpanBufBytes) + (uint32_t)lane * RAWP + k * (SUB * 2u);
             } else {
               mbar_wait(&pc->ab_full[slot], (use & 1u) ^ 1u);
-              src = ya;
+              mbar_wait(&pc->free2[slot], use & 1u);
+              src = smem_u32(sSlot + slot * kSlotBytes) + (uint32_t)lane * (EW * 4u);
             }
             prof.lap(0);
             uint4 nx = lds128(src);
@@ -666,7 +673,10 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
               }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(isF1 ? &pc->ld_full[slot] : &pc->m_full[slot]);
+            if (lane == 0) {
+              mbar_arrive(isF1 ? &pc->ld_full[slot] : &pc->m_full[slot]);
+              if (!isF1) mbar_arrive(&pc->slot_free[slot]); // ring 1's slot has been read
+            }
             prof.lap(1);
           }
           if (isF1) {
@@ -689,20 +699,20 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
       uint32_t rows[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) rows[i] = __ldg(rmap + r0 + 4 * i);
-      for (uint32_t k = 0; k < nsub; ++k, slot = (slot + 1 == NSL ? 0 : slot + 1), use += (slot == 0)) {
+      for (uint32_t k = 0; k < nsub; ++k, slot = (slot + 1 == NH ? 0 : slot + 1), use += (slot == 0)) {
         prof.start();
         mbar_wait(&pc->st_full[slot], (use & 1u) ^ 1u);
         prof.lap(0);
-        const uint32_t sa = smem_u32(sSlot + slot * kSlotBytes) + (uint32_t)(G * EW * 4) + (uint32_t)r0 * (YW * 4u) + (uint32_t)c * 16u;
+        const uint32_t sa = smem_u32(sSlot + (NH + slot) * kSlotBytes) + (uint32_t)r0 * (EW * 4u) + (uint32_t)c * 16u; // ring 2; the int16 results are the front 128 bytes of a row
         const uint32_t col16 = k * (SUB / 8) + (uint32_t)c;
         uint4 v[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = lds128(sa + (uint32_t)i * 4u * (YW * 4u));
+        for (int i = 0; i < 8; ++i) v[i] = lds128(sa + (uint32_t)i * 4u * (EW * 4u));
 #pragma unroll
         for (int i = 0; i < 8; ++i)
           if (rows[i] != kPad) out16[(size_t)rows[i] * stride16 + col16] = v[i];
         __syncwarp();
-        if (lane == 0) mbar_arrive(&pc->slot_free[slot]);
+        if (lane == 0) mbar_arrive(&pc->free2[slot]);
         prof.lap(1);
       }
     }
@@ -712,11 +722,11 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
 
 } // namespace v6
 
-// number of sub-tile slots (6..8) that fit next to the operand buffers of window K; 0 = this window is too long for the kernel
+// number of sub-tile slots (both rings: 8, 10 or 12) that fit next to the operand buffers of window K; 0 = this window is too long for the kernel
 uint32_t chain_v6_config(uint32_t K, int smem_max)
 {
   if (K % 32u || K / 32u < 2u) return 0;
-  for (uint32_t n = v6::NSLOT_MAX; n >= 6u; --n)
+  for (uint32_t n = v6::NSLOT_MAX; n >= 8u; n -= 2u) // an even count: two rings of at least four slots
     if (v6::smem_bytes(K, n) <= (size_t)smem_max) return n;
   return 0;
 }
@@ -729,7 +739,7 @@ cudaError_t launch_chain_v6(const ChainParams &p_in, cudaStream_t stream, int va
   p.ablate = ((uint32_t)variant >> 4) & 3u;
   if (const char *ev = getenv("MSDR_ABLATE")) p.ablate |= (uint32_t)atoi(ev) & ~3u; // study only: 4 = no demodulation, 8 = no TMEM drain (results are wrong)
   const size_t smem = smem_bytes(p.tc_K, p.tc_ring);
-  auto kern = (variant & 2) ? chain_kernel<BqFFI> : chain_kernel<BqFF>; // study knob: bit 1 = feed-forward products as IMAD.HI instead of DFMA
+  auto kern = (variant & 2) ? chain_kernel<BqFF> : chain_kernel<BqFFI>; // study knob: bit 1 = feed-forward products as DFMA instead of IMAD.HI
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const uint32_t grid = p.n_items < (uint32_t)sms ? p.n_items : (uint32_t)sms;
