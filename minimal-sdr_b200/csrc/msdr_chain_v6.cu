@@ -46,7 +46,7 @@ using v5::demod_regs;
 
 constexpr int kWarps = 16;
 constexpr int kThreads = kWarps * 32;
-constexpr int kChainA = 4, kChainB = 5, kMmaWarp = 6, kLoadWarp = 7, kStoreWarp = 8, kFF1 = 10, kFF2 = 11, kConv0 = 14;
+constexpr int kChainA = 4, kChainB = 5, kMmaWarp = 6, kLoadWarp = 7, kStoreWarp = 9, kFF1 = 10, kFF2 = 11, kConv0 = 14;
 constexpr int kConvThreads = 64;
 constexpr int G = 32;             // channels of a group block (one chain warp)
 constexpr int HR = 16;            // channels of a tile
