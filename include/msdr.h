@@ -148,8 +148,11 @@ int msdr_chain_get_state(msdr_chain *chain, uint32_t ch, msdr_channel_state *out
 int msdr_chain_set_state(msdr_chain *chain, uint32_t ch, const msdr_channel_state *in);
 
 /* Options.  "variant" selects the shape of the fused kernel for studies and cross-checks (all shapes are bit-exact):
- *   0    default: tensor-core FIR producers (tcgen05 kind::i8) + pinned biquad chains; feed-forward helper warps up to 148
- *        channel groups, two chain sets per SM beyond
+ *   0    default, by channel count: the time-folded kernel (msdr_chain_v6.cu) up to one 32-channel group block per SM; tensor-core
+ *        FIR producers (tcgen05 kind::i8) + pinned biquad chains (msdr_chain_v4.cu: feed-forward helper warps up to 148 channel
+ *        groups, two chain sets per SM beyond) up to 12 287 channels; the row-block kernels (msdr_chain_v5.cu / v5l.cu) from there
+ *   16384  never the time-folded kernel;  65536  the time-folded kernel for any channel count;  +2 there: feed-forward products as DFMA
+ *   8192   never the row-block kernel;    4096   the row-block kernel for any channel count;    32768  its half-tile form for any window
  *   64   CUDA-core FIR kernel (msdr_chain_v3.cu); +1: biquad products on the FP64 pipe; +8: two channels per chain lane
  *   128  helper-warp shape even beyond 148 groups;  2048: post-warp shape (whole stages in the chain warps);
  *   256  classic shape (neither helper nor post warps)
