@@ -251,6 +251,36 @@ __device__ __forceinline__ void bq_store_stage(const BqStageE &s, uint32_t flag,
   b[7 * (size_t)Cpad] = (int32_t)((uint32_t)s.res | flag);
 }
 
+template <int NS>
+__device__ __forceinline__ uint32_t bq_word(BqStageS (&st)[NS], uint32_t w)
+{
+  static_assert(NS == 1, "the split stage takes plain values in and hands y << 16 out: single stages only");
+  int xe, xo;
+  asm("prmt.b32 %0, %1, 0, 0x9910;" : "=r"(xe) : "r"(w));
+  asm("prmt.b32 %0, %1, 0, 0xBB32;" : "=r"(xo) : "r"(w));
+  xe = bq_step(st[0], xe);
+  xo = bq_step(st[0], xo);
+  return __byte_perm((uint32_t)xe, (uint32_t)xo, 0x7632);
+}
+__device__ __forceinline__ void bq_load_stage(BqStageS &s, uint32_t &flag, const int32_t *__restrict__ bq, uint32_t Cpad, int obj, int stage, uint32_t ch)
+{
+  const int32_t *b = bq + (size_t)((obj * 4 + stage) * 8) * Cpad + ch;
+  bq_set_coefs(s, __ldcg(b + 0 * (size_t)Cpad), __ldcg(b + 1 * (size_t)Cpad), __ldcg(b + 2 * (size_t)Cpad), __ldcg(b + 3 * (size_t)Cpad),
+               __ldcg(b + 4 * (size_t)Cpad));
+  const uint32_t w5 = (uint32_t)__ldcg(b + 5 * (size_t)Cpad), w6 = (uint32_t)__ldcg(b + 6 * (size_t)Cpad);
+  s.x1 = (int)w5 >> 16; s.x2 = (int)(short)(w5 & 0xFFFFu);
+  s.y1s = (int)(w6 & 0xFFFF0000u); s.y2 = (int)(short)(w6 & 0xFFFFu);
+  const uint32_t w7 = (uint32_t)__ldcg(b + 7 * (size_t)Cpad);
+  s.res = (int)(w7 & 0x3FFFu);
+  flag = w7 & 0x80000000u;
+}
+__device__ __forceinline__ void bq_store_stage(const BqStageS &s, uint32_t flag, int32_t *__restrict__ bq, uint32_t Cpad, int obj, int stage, uint32_t ch)
+{
+  int32_t *b = bq + (size_t)((obj * 4 + stage) * 8) * Cpad + ch;
+  b[5 * (size_t)Cpad] = (int32_t)(((uint32_t)s.x1 << 16) | ((uint32_t)s.x2 & 0xFFFFu));
+  b[6 * (size_t)Cpad] = (int32_t)(((uint32_t)s.y1s & 0xFFFF0000u) | ((uint32_t)s.y2 & 0xFFFFu));
+  b[7 * (size_t)Cpad] = (int32_t)((uint32_t)s.res | flag);
+}
 __device__ __forceinline__ void bq_load_stage(BqStage &s, uint32_t &flag, const int32_t *__restrict__ bq, uint32_t Cpad, int obj, int stage, uint32_t ch)
 {
   const int32_t *b = bq + (size_t)((obj * 4 + stage) * 8) * Cpad + ch;

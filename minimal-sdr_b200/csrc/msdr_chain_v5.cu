@@ -430,7 +430,7 @@ cudaError_t launch_chain_v5(const ChainParams &p_in, cudaStream_t stream, int va
   const size_t smem = smem_bytes(p.tc_K, p.tc_ring);
   // study knobs: variant bit 0 = all five products as IMAD.HI, bit 1 = feed-forward products as DFMA; default = IMAD.WIDE for the
   // four products off the recurrence
-  auto kern = (variant & 1) ? chain_kernel<BqStage> : (variant & 2) ? chain_kernel<BqStageH> : (variant & 4) ? chain_kernel<BqStageC> : (variant & 8) ? chain_kernel<BqStageE> : chain_kernel<BqStageW>;
+  auto kern = (variant & 12) == 12 ? chain_kernel<BqStageS> : (variant & 1) ? chain_kernel<BqStage> : (variant & 2) ? chain_kernel<BqStageH> : (variant & 4) ? chain_kernel<BqStageC> : (variant & 8) ? chain_kernel<BqStageE> : chain_kernel<BqStageW>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const uint32_t grid = p.n_items < (uint32_t)sms ? p.n_items : (uint32_t)sms;

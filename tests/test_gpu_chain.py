@@ -307,7 +307,8 @@ def test_update_range_device(msdr, orc, K):
                                             (256, "tensor-core FIR, inline epilogue"), (128, "helper warps, forced"), (64, "CUDA-core FIR (v3)"),
                                             (65, "v3, FP64 biquad"), (4096, "row-block kernel (msdr_chain_v5.cu), forced"),
                                             (4097, "row-block kernel, IMAD.HI stages"), (4098, "row-block kernel, DFMA feed-forward"),
-                                            (4100, "row-block kernel, chained DFMA feed-forward"), (4104, "row-block kernel, all five products one DFMA chain")])
+                                            (4100, "row-block kernel, chained DFMA feed-forward"), (4104, "row-block kernel, all five products one DFMA chain"),
+                                            (4108, "row-block kernel, split 16 x 16-bit products")])
 def test_every_kernel_shape_is_bit_exact(msdr, orc, K, variant, name):
     """All shapes of the fused kernel (option "variant") produce the oracle's bits: mixed modes, ragged updates, 4-stage cascades on
     some channels, full-range (wrapping) taps on others, extreme inputs, a partial last group."""
