@@ -858,7 +858,9 @@ int msdr_chain_update_range_device(msdr_chain *chain, uint32_t ch0, uint32_t nch
     // Many channels: the row-block kernel (msdr_chain_v5.cu), one CTA per 128 channels of one tap table walking through time.  It
     // needs enough row blocks to fill the SMs (kV5MinChannels: below that the pinned chains of msdr_chain_v4.cu win);
     // variant bit 12 forces it for any channel count (parity tests), bit 13 forbids it.
-    constexpr uint32_t kV5MinChannels = 12288;
+    // (more channel groups than one wave of two chain sets per SM holds - 9472 channels on 148 SMs - would make msdr_chain_v4.cu walk a
+    // second, mostly empty wave: 11 264 channels 172 Gsamples/s there against ~200 here)
+    const uint32_t kV5MinChannels = std::min<uint32_t>(12288u, 2u * (uint32_t)sms * (uint32_t)kGroup + 1u);
     bool use_v5 = ((chain->variant & 4096) || nch >= kV5MinChannels) && !(chain->variant & (8192 | 128 | 256 | 512 | 2048));
     if (use_v5) { // does the longest live table's window fit that kernel at all?  (known without sorting a single row: 256 taps do not)
       int smem_max = 0;

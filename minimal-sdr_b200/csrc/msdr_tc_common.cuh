@@ -143,7 +143,11 @@ __device__ __forceinline__ uint32_t pack_sat_iq(int I, int Q)
 }
 __device__ __forceinline__ void drain_tile(uint32_t lane_addr, uint32_t *orow)
 {
+#ifdef MSDR_DRAIN_UNROLLED
 #pragma unroll
+#else
+#pragma unroll 1 // eight passes of eight columns as a loop: 650 instructions of straight-line code per tile and warp otherwise (instruction caches)
+#endif
   for (int c0 = 0; c0 < N; c0 += 8) {
     uint32_t acc[2 * kAccPerBranch][8]; // [branch*3 + part][column]
 #pragma unroll
