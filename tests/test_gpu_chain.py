@@ -185,6 +185,29 @@ def test_long_taps_256(msdr, orc, K, variant):
     assert ("v5l" in g.last_kernel()) == bool(variant & 4096)
 
 
+@pytest.mark.parametrize("taps", [30, 150, 200, 250])
+def test_window_sizes_on_the_time_folded_kernel(msdr, orc, K, taps):
+    """The time-folded kernel (msdr_chain_v6.cu) sizes its operand buffers, its Toeplitz operands and the number of sub-tile slots from
+    the window: 30 taps (the shortest window), 150 and 200 (128 words), 250 (160 words, the longest it takes; 256 taps go to the chain
+    kernel).  Six tables over 35 channels: half blocks are mostly padding and pair up across tables; mixed modes, wrapping
+    taps on some channels, one-block and odd-length updates (a span is 256 samples: the last one is half empty)."""
+    rng = np.random.default_rng(taps)
+    modes = [AM, USB, LSB, CW, USB] * 7
+    six = []
+    for k in range(6):
+        if k % 3 == 0:
+            six.append((wrap_coeffs(taps, rng), wrap_coeffs(taps, rng)))
+        else:
+            cI = rng.integers(-700, 700, taps).astype(np.int16)
+            six.append((cI, cI[::-1].copy()))
+    tabs = {c: six[(c * 5) % 6] for c in range(len(modes))}
+    x = np.stack([rng.integers(-32768, 32768, 128 * 23, dtype=np.int16) for _ in modes])
+    g, o = configure_pair(msdr, orc, K, modes, max_taps=taps, tables=tabs)
+    yg, yo = run_pair(g, o, x, splits=[1, 3, 1, 2, 16])
+    assert_same(yg, yo, f"{taps} taps")
+    assert "v6::" in g.last_kernel(), g.last_kernel()
+
+
 def test_errors_match_reference_conventions(msdr, K):
     g = msdr.ReceiveChain(8)
     am = np.array(K["FIR_AM_coeffs_bw2800_fs24000"], np.int16)
