@@ -130,12 +130,20 @@ struct msdr_chain {
     uint8_t *d_kind = nullptr, *d_anr_mode = nullptr;
     bool any_pll = false, any_anr = false;
     bool dirty = true;                 // modes / ANR switches changed: rebuild `channels`
+    uint64_t epoch = 0;                // counts those changes
+    // the index vectors of the last update's range stay valid (host copies persist: their uploads are asynchronous)
+    bool cached = false;
+    uint64_t key_epoch = 0, key_version = 0;
+    uint32_t key_ch0 = 0, key_nch = 0;
+    std::vector<uint32_t> chmap;
+    std::vector<uint8_t> kind, amode;
     std::vector<uint32_t> channels;    // every chain channel that needs the lane, ascending
     int16_t *d_raw = nullptr, *d_I = nullptr, *d_Q = nullptr, *d_If = nullptr, *d_Qf = nullptr, *d_taps = nullptr;
     int32_t *d_defs = nullptr;
     size_t cap_rows = 0, cap_samples = 0;
   } pll;
 
+  int16_t *d_set_taps = nullptr;     // [MSDR_MAX_FIR_SETS][2][MSDR_MAX_TAPS] every live table's raw taps (the side lane's FIR launches read them)
   int variant = 0;
   uint32_t host_chunk_channels = 0, host_chunk_blocks = 0; // 0 = auto
   uint32_t spare_sms = 0;
@@ -186,6 +194,12 @@ int upload_set(msdr_chain *chain, uint32_t id)
   CK(cudaMemcpyAsync(chain->d_sets + (size_t)id * chain->set_stride_words, ex.data(), ex.size() * sizeof(int32_t), cudaMemcpyHostToDevice,
                      chain->stream));
   CK(cudaMemcpyAsync(chain->d_set_kp4 + id, &kp4, sizeof(kp4), cudaMemcpyHostToDevice, chain->stream));
+  {
+    const FirSet &fs = chain->sets[id];
+    int16_t *dst = chain->d_set_taps + (size_t)id * 2 * MSDR_MAX_TAPS;
+    CK(cudaMemcpyAsync(dst, fs.cI.data(), fs.T * 2, cudaMemcpyHostToDevice, chain->stream));
+    CK(cudaMemcpyAsync(dst + MSDR_MAX_TAPS, fs.cQ.data(), fs.T * 2, cudaMemcpyHostToDevice, chain->stream));
+  }
   CK(cudaStreamSynchronize(chain->stream)); // `ex` and `kp4` are stack/heap temporaries
   chain->meta_version++;
   return MSDR_OK;
@@ -298,6 +312,7 @@ int msdr_chain_create(msdr_chain **out, int device, uint32_t n_channels, uint32_
   CKC(cudaMemsetAsync(chain->d_pll, 0, (size_t)3 * chain->Cpad * sizeof(float), chain->own_stream));
   CKC(cudaMalloc(&chain->d_sets, (size_t)MSDR_MAX_FIR_SETS * chain->set_stride_words * sizeof(int32_t)));
   CKC(cudaMalloc(&chain->d_set_kp4, MSDR_MAX_FIR_SETS * sizeof(uint32_t)));
+  CKC(cudaMalloc(&chain->d_set_taps, (size_t)MSDR_MAX_FIR_SETS * 2 * MSDR_MAX_TAPS * sizeof(int16_t)));
   CKC(cudaMalloc(&chain->d_ctrl, (size_t)(1 + chain->Cpad / kGroup + 1) * sizeof(int)));
   CKC(cudaMemsetAsync(chain->d_mode, MSDR_MODE_AM, n_channels, chain->stream));
   CKC(cudaMemsetAsync(chain->d_set, 0, n_channels, chain->stream));
@@ -323,7 +338,7 @@ void msdr_chain_destroy(msdr_chain *chain)
   cudaFree(chain->pll.d_kind); cudaFree(chain->pll.d_anr_mode);
   cudaFree(chain->pll.d_rows); cudaFree(chain->pll.d_chmap); cudaFree(chain->pll.d_raw); cudaFree(chain->pll.d_I); cudaFree(chain->pll.d_Q);
   cudaFree(chain->pll.d_If); cudaFree(chain->pll.d_Qf); cudaFree(chain->pll.d_taps); cudaFree(chain->pll.d_defs);
-  cudaFree(chain->d_sets); cudaFree(chain->d_set_kp4); cudaFree(chain->d_ctrl); cudaFree(chain->d_tile_flags);
+  cudaFree(chain->d_sets); cudaFree(chain->d_set_kp4); cudaFree(chain->d_set_taps); cudaFree(chain->d_ctrl); cudaFree(chain->d_tile_flags);
   cudaFree(chain->d_in); cudaFree(chain->d_out);
   if (chain->pin_in) cudaFreeHost(chain->pin_in);
   if (chain->pin_out) cudaFreeHost(chain->pin_out);
@@ -372,7 +387,7 @@ int msdr_chain_set_mode(msdr_chain *chain, uint32_t ch0, uint32_t nch, int mode)
   if (nch == 0) return MSDR_OK;
   CK(cudaSetDevice(chain->device));
   std::fill(chain->h_mode.begin() + ch0, chain->h_mode.begin() + ch0 + nch, (uint8_t)mode);
-  chain->pll.dirty = true;
+  chain->pll.dirty = true; chain->pll.epoch++;
   CK(cudaMemsetAsync(chain->d_mode + ch0, mode, nch, chain->stream));
   return MSDR_OK;
 }
@@ -399,7 +414,7 @@ int msdr_chain_set_anr(msdr_chain *chain, uint32_t ch0, uint32_t nch, int anr_on
     chain->n_anr += (anr_on != 0) - (chain->h_anr[c] != 0);
     chain->h_anr[c] = (uint8_t)anr_on; // the LMS state is kept across on/off like the sketch's statics
   }
-  chain->pll.dirty = true;
+  chain->pll.dirty = true; chain->pll.epoch++;
   return MSDR_OK;
 }
 
@@ -477,7 +492,7 @@ int msdr_chain_set_mode_list(msdr_chain *chain, const uint32_t *channels, uint32
   }
   CK(cudaSetDevice(chain->device));
   for (uint32_t i = 0; i < n; ++i) chain->h_mode[channels[i]] = (uint8_t)mode;
-  chain->pll.dirty = true;
+  chain->pll.dirty = true; chain->pll.epoch++;
   CK(cudaMemcpyAsync(chain->d_mode + lo, chain->h_mode.data() + lo, hi - lo + 1, cudaMemcpyHostToDevice, chain->stream));
   CK(cudaStreamSynchronize(chain->stream));
   return MSDR_OK;
@@ -719,55 +734,62 @@ namespace {
 int syncam_lane_prepare(msdr_chain *chain, uint32_t ch0, uint32_t nch, const int16_t *d_in, size_t stride, uint32_t L)
 {
   msdr_chain::PllLane &ln = chain->pll;
-  ln.rows.clear();
-  ln.any_pll = ln.any_anr = false;
   const bool pll_build = !(chain->flags & MSDR_FLAG_AM_Q31); // Teensy 3.2 arithmetic: SYNCAM is the q31 envelope (.ino:618-620)
-  if (ln.dirty) { // one scan per configuration change, not per update
-    ln.channels.clear();
-    for (uint32_t c = 0; c < chain->C; ++c)
-      if ((pll_build && chain->h_mode[c] == MSDR_MODE_SYNCAM) || (chain->n_anr && chain->h_anr[c] != 0)) ln.channels.push_back(c);
-    ln.dirty = false;
-  }
-  if (ln.channels.empty()) return MSDR_OK;
-  for (auto it = std::lower_bound(ln.channels.begin(), ln.channels.end(), ch0); it != ln.channels.end() && *it < ch0 + nch; ++it) {
-    const uint32_t r = *it - ch0;
-    const bool is_pll = pll_build && chain->h_mode[ch0 + r] == MSDR_MODE_SYNCAM;
-    const bool is_anr = chain->n_anr && chain->h_anr[ch0 + r] != 0;
-    ln.rows.push_back(r);
-    ln.any_pll |= is_pll; ln.any_anr |= is_anr;
+  // The lane's index vectors depend on the range, the modes / ANR switches (epoch) and the table bindings (meta_version) only: an update
+  // that repeats the last one's configuration re-uses them on the device, and nothing in this function waits for the stream.
+  const bool hit = ln.cached && ln.key_epoch == ln.epoch && ln.key_version == chain->meta_version && ln.key_ch0 == ch0 && ln.key_nch == nch;
+  if (!hit) {
+    ln.rows.clear();
+    ln.any_pll = ln.any_anr = false;
+    if (ln.dirty) { // one scan per configuration change, not per update
+      ln.channels.clear();
+      for (uint32_t c = 0; c < chain->C; ++c)
+        if ((pll_build && chain->h_mode[c] == MSDR_MODE_SYNCAM) || (chain->n_anr && chain->h_anr[c] != 0)) ln.channels.push_back(c);
+      ln.dirty = false;
+    }
+    for (auto it = std::lower_bound(ln.channels.begin(), ln.channels.end(), ch0); it != ln.channels.end() && *it < ch0 + nch; ++it) {
+      const uint32_t r = *it - ch0;
+      const bool is_pll = pll_build && chain->h_mode[ch0 + r] == MSDR_MODE_SYNCAM;
+      const bool is_anr = chain->n_anr && chain->h_anr[ch0 + r] != 0;
+      ln.rows.push_back(r);
+      ln.any_pll |= is_pll; ln.any_anr |= is_anr;
+    }
+    std::stable_sort(ln.rows.begin(), ln.rows.end(), [&](uint32_t a, uint32_t b) { return chain->h_set[ch0 + a] < chain->h_set[ch0 + b]; });
+    ln.cached = true; ln.key_epoch = ln.epoch; ln.key_version = chain->meta_version; ln.key_ch0 = ch0; ln.key_nch = nch;
   }
   if (ln.rows.empty()) return MSDR_OK;
-  std::stable_sort(ln.rows.begin(), ln.rows.end(), [&](uint32_t a, uint32_t b) { return chain->h_set[ch0 + a] < chain->h_set[ch0 + b]; });
   const uint32_t n = (uint32_t)ln.rows.size();
   const size_t Lp = (size_t)chain->H + L, samples = (size_t)n * Lp;
+  bool upload = !hit;
   if (n > ln.cap_rows || samples > ln.cap_samples) {
     CK(cudaStreamSynchronize(chain->stream));
-    cudaFree(ln.d_rows); cudaFree(ln.d_chmap); cudaFree(ln.d_raw); cudaFree(ln.d_I); cudaFree(ln.d_Q); cudaFree(ln.d_If); cudaFree(ln.d_Qf); cudaFree(ln.d_taps);
+    cudaFree(ln.d_rows); cudaFree(ln.d_chmap); cudaFree(ln.d_raw); cudaFree(ln.d_I); cudaFree(ln.d_Q); cudaFree(ln.d_If); cudaFree(ln.d_Qf);
     cudaFree(ln.d_defs); cudaFree(ln.d_kind); cudaFree(ln.d_anr_mode);
     ln.d_kind = ln.d_anr_mode = nullptr;
-    ln.d_rows = ln.d_chmap = nullptr; ln.d_raw = ln.d_I = ln.d_Q = ln.d_If = ln.d_Qf = ln.d_taps = nullptr; ln.d_defs = nullptr;
+    ln.d_rows = ln.d_chmap = nullptr; ln.d_raw = ln.d_I = ln.d_Q = ln.d_If = ln.d_Qf = nullptr; ln.d_defs = nullptr;
     ln.cap_rows = ln.cap_samples = 0;
     CK(cudaMalloc(&ln.d_rows, n * 4)); CK(cudaMalloc(&ln.d_chmap, n * 4)); CK(cudaMalloc(&ln.d_kind, n)); CK(cudaMalloc(&ln.d_anr_mode, n)); CK(cudaMalloc(&ln.d_defs, (size_t)n * 64 * 4));
-    CK(cudaMalloc(&ln.d_taps, 2 * MSDR_MAX_TAPS * sizeof(int16_t)));
     CK(cudaMalloc(&ln.d_raw, samples * 2)); CK(cudaMalloc(&ln.d_I, samples * 2)); CK(cudaMalloc(&ln.d_Q, samples * 2));
     CK(cudaMalloc(&ln.d_If, samples * 2)); CK(cudaMalloc(&ln.d_Qf, samples * 2));
     ln.cap_rows = n; ln.cap_samples = samples;
+    upload = true;
   }
-  std::vector<uint32_t> chmap(n);
-  std::vector<uint8_t> kind(n), amode(n);
-  for (uint32_t i = 0; i < n; ++i) {
-    const uint32_t ch = ch0 + ln.rows[i];
-    chmap[i] = ch;
-    const int md = chain->h_mode[ch];
-    // demodulation kind of the row (Minimal-SDR.ino:589-628); 255 = the PLL demodulator takes the row
-    kind[i] = (pll_build && md == MSDR_MODE_SYNCAM) ? 255 : md == MSDR_MODE_LSB ? 0 : md == MSDR_MODE_USB ? 1 : (md == MSDR_MODE_SYNCAM || !pll_build) ? 3 : 2;
-    amode[i] = chain->n_anr ? chain->h_anr[ch] : 0;
+  if (upload) {
+    ln.chmap.resize(n); ln.kind.resize(n); ln.amode.resize(n);
+    for (uint32_t i = 0; i < n; ++i) {
+      const uint32_t ch = ch0 + ln.rows[i];
+      ln.chmap[i] = ch;
+      const int md = chain->h_mode[ch];
+      // demodulation kind of the row (Minimal-SDR.ino:589-628); 255 = the PLL demodulator takes the row
+      ln.kind[i] = (pll_build && md == MSDR_MODE_SYNCAM) ? 255 : md == MSDR_MODE_LSB ? 0 : md == MSDR_MODE_USB ? 1 : (md == MSDR_MODE_SYNCAM || !pll_build) ? 3 : 2;
+      ln.amode[i] = chain->n_anr ? chain->h_anr[ch] : 0;
+    }
+    // pageable sources: the copies are staged before these calls return, and the vectors live in the lane until the next rebuild
+    CK(cudaMemcpyAsync(ln.d_rows, ln.rows.data(), n * 4, cudaMemcpyHostToDevice, chain->stream));
+    CK(cudaMemcpyAsync(ln.d_chmap, ln.chmap.data(), n * 4, cudaMemcpyHostToDevice, chain->stream));
+    CK(cudaMemcpyAsync(ln.d_kind, ln.kind.data(), n, cudaMemcpyHostToDevice, chain->stream));
+    CK(cudaMemcpyAsync(ln.d_anr_mode, ln.amode.data(), n, cudaMemcpyHostToDevice, chain->stream));
   }
-  CK(cudaMemcpyAsync(ln.d_rows, ln.rows.data(), n * 4, cudaMemcpyHostToDevice, chain->stream));
-  CK(cudaMemcpyAsync(ln.d_chmap, chmap.data(), n * 4, cudaMemcpyHostToDevice, chain->stream));
-  CK(cudaMemcpyAsync(ln.d_kind, kind.data(), n, cudaMemcpyHostToDevice, chain->stream));
-  CK(cudaMemcpyAsync(ln.d_anr_mode, amode.data(), n, cudaMemcpyHostToDevice, chain->stream));
-  CK(cudaStreamSynchronize(chain->stream)); // the index vectors are temporaries / reused host storage
   CK(launch_gather_rows(ln.d_rows, n, ch0, chain->d_hist, chain->H, d_in, stride, ln.d_raw, L, chain->stream));
   CK(launch_bq_words(0, ln.d_rows, n, ch0, chain->d_bq, chain->Cpad, ln.d_defs, chain->stream));
   chain->launches += 2;
@@ -786,11 +808,9 @@ int syncam_lane_finish(msdr_chain *chain, uint32_t ch0, int16_t *d_out, size_t s
     uint32_t i1 = i0;
     while (i1 < n && chain->h_set[ch0 + ln.rows[i1]] == sid) ++i1;
     const FirSet &fs = chain->sets[sid];
-    CK(cudaMemcpyAsync(ln.d_taps, fs.cI.data(), fs.T * 2, cudaMemcpyHostToDevice, chain->stream));
-    CK(cudaMemcpyAsync(ln.d_taps + MSDR_MAX_TAPS, fs.cQ.data(), fs.T * 2, cudaMemcpyHostToDevice, chain->stream));
-    CK(launch_fir_fast_q15(fs.T, ln.d_taps, nullptr, nullptr, ln.d_I + i0 * Lp, ln.d_If + i0 * Lp, i1 - i0, (uint32_t)Lp, Lp, chain->stream));
-    CK(launch_fir_fast_q15(fs.T, ln.d_taps + MSDR_MAX_TAPS, nullptr, nullptr, ln.d_Q + i0 * Lp, ln.d_Qf + i0 * Lp, i1 - i0, (uint32_t)Lp, Lp, chain->stream));
-    CK(cudaStreamSynchronize(chain->stream)); // d_taps is reused by the next table
+    const int16_t *taps = chain->d_set_taps + (size_t)sid * 2 * MSDR_MAX_TAPS; // resident since upload_set: no copy, no wait per table
+    CK(launch_fir_fast_q15(fs.T, taps, nullptr, nullptr, ln.d_I + i0 * Lp, ln.d_If + i0 * Lp, i1 - i0, (uint32_t)Lp, Lp, chain->stream));
+    CK(launch_fir_fast_q15(fs.T, taps + MSDR_MAX_TAPS, nullptr, nullptr, ln.d_Q + i0 * Lp, ln.d_Qf + i0 * Lp, i1 - i0, (uint32_t)Lp, Lp, chain->stream));
     chain->launches += 2;
     i0 = i1;
   }

@@ -437,6 +437,42 @@ def test_anr_channels_in_a_chain(msdr, orc, K):
     assert np.abs(a - b).max() <= 3 and np.sqrt(np.mean((a - b) ** 2)) <= 1e-4 * np.sqrt(np.mean(b ** 2)) + 0.05
 
 
+def test_side_lane_is_cached_and_asynchronous(msdr, orc, K):
+    """Channels with the LMS notch on are finished beside the fused kernel; the lane's index vectors are cached per range and
+    configuration and nothing waits for the stream.  Device-resident updates queued back to back on one stream without a host sync in
+    between: the same range repeated (cache hits), two ranges alternating (misses that overwrite the cached vectors while earlier lane
+    kernels are still queued), the ANR switch of a channel changed between updates (invalidation).  Bit-exact against the oracle."""
+    import torch
+    modes = msdr.synth.mixed_modes(96)
+    nb = [3, 2, 4, 3]
+    x = msdr.synth.batch(modes, 128 * sum(nb))
+    g, o = configure_pair(msdr, orc, K, modes)
+    anr = {1: 1, 2: 2, 40: 1, 63: 2, 64: 1, 95: 2}
+    for c, v in anr.items():
+        g.set_anr(v, c, 1)
+        assert o.set_anr(c, 1, v) == 0
+    d_in = torch.from_numpy(x).cuda()
+    d_out = torch.zeros_like(d_in)
+    st = torch.cuda.Stream()
+    g.set_stream(st.cuda_stream)
+    parts, b0 = [], 0
+    for i, n in enumerate(nb):
+        if i == 2:  # between updates: one channel's notch off, another one on
+            g.synchronize()
+            g.set_anr(0, 40, 1); g.set_anr(1, 41, 1)
+            assert o.set_anr(40, 1, 0) == 0 and o.set_anr(41, 1, 1) == 0
+        col = b0 * 128
+        if i == 1:  # the whole chain in one call, twice the same range afterwards
+            g.update_range_device(0, 96, d_in[:, col:].data_ptr(), d_out[:, col:].data_ptr(), n, d_in.stride(0))
+        else:       # two ranges alternating
+            for c0, cn in ((64, 32), (0, 64)):
+                g.update_range_device(c0, cn, d_in[c0:, col:].data_ptr(), d_out[c0:, col:].data_ptr(), n, d_in.stride(0))
+        parts.append(o.run(np.ascontiguousarray(x[:, col:col + n * 128]))[0])
+        b0 += n
+    g.synchronize()
+    assert_same(d_out.cpu().numpy(), np.concatenate(parts, axis=1), "side lane, cached index vectors")
+
+
 def test_whole_file_on_the_chain_kernel():
     """The time-folded kernel (msdr_chain_v6.cu) is the default for few channels, so this file runs on it; MSDR_VARIANT=16384 forbids it
     and the chain tests run again on the chain kernel (msdr_chain_v4.cu), which still serves the channel counts between the two
