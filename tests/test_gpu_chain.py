@@ -205,7 +205,8 @@ def test_window_sizes_on_the_time_folded_kernel(msdr, orc, K, taps):
     g, o = configure_pair(msdr, orc, K, modes, max_taps=taps, tables=tabs)
     yg, yo = run_pair(g, o, x, splits=[1, 3, 1, 2, 16])
     assert_same(yg, yo, f"{taps} taps")
-    assert "v6::" in g.last_kernel(), g.last_kernel()
+    if not os.environ.get("MSDR_VARIANT"):  # (the whole-file re-runs force another kernel through the environment)
+        assert "v6::" in g.last_kernel(), g.last_kernel()
 
 
 def test_errors_match_reference_conventions(msdr, K):
