@@ -486,8 +486,26 @@ def main():
             torch.cuda.synchronize()
             pc[name + "_gbs"] = 3 * nrow * Le * 2 / (time.perf_counter() - t0) / 1e9
             barrier()
-        del dbuf
+        # both directions at once on two streams (what the end-to-end path asks of the link): the roofline of `e2e`
+        dbuf2 = torch.empty((nrow, Le), dtype=torch.int16, device=dev)
+        s_up, s_dn = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+        def both():
+            with torch.cuda.stream(s_up):
+                dbuf.copy_(th[:nrow], non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                to[:nrow].copy_(dbuf2, non_blocking=True)
+        both()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            both()
+        torch.cuda.synchronize()
+        pc["both_gbs_each_way"] = 3 * nrow * Le * 2 / (time.perf_counter() - t0) / 1e9
+        barrier()
+        del dbuf, dbuf2
         pc["e2e_gbs_each_way"] = C * Le * 2 * args.e2e_steps / dt_local / 1e9
+        pc["e2e_over_link_both_ways"] = pc["e2e_gbs_each_way"] / pc["both_gbs_each_way"]
         pc["pinned"] = bool(th.is_pinned())
         e2e["pcie_this_rank"] = pc
         if parity is not None:  # the same call on a fresh chain, sampled channels against the CPU checker over the whole call
