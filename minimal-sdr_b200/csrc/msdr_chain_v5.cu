@@ -28,6 +28,8 @@
 // Every sub-partition hosts two epilogue warps, one warp of each biquad object and one converter: the TMEM read port (64 B/clk per
 // SM, 24 B per output sample for the six int32 accumulators), the integer multiplier (5 IMAD.HI per sample and stage) and the issue
 // slots are all used evenly.
+#include <cstdlib>
+#include <type_traits>
 #include "msdr_chain_v5_common.cuh"
 
 namespace msdr {
@@ -348,6 +350,17 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
       }
       const bool fast = __all_sync(0xffffffffu, nst == 1);
       if (fast && active) bq_load_stage(st[0], fl, p.bq, p.Cpad, obj, 0, ch);
+      // symmetric numerators (b0 == b2) in every lane: the four-product form of the stage (msdr_device.cuh: BqStageWS)
+      bool sym = false;
+      BqStageWS ss[1];
+      if constexpr (std::is_same<BQ, BqStageW>::value) {
+        sym = fast && !(p.ablate & 4u) && __all_sync(0xffffffffu, !active || st[0].b0 == st[0].b2);
+        if (sym && active) {
+          static_cast<BqStage &>(ss[0]) = static_cast<const BqStage &>(st[0]);
+          ss[0].p1 = mulhi_wide(st[0].b0, st[0].x1);
+          ss[0].p2 = mulhi_wide(st[0].b0, st[0].x2);
+        }
+      }
       for (uint32_t t = 0; t < NT; ++t, ++tseq) {
         const uint32_t slot = tseq % NS, phs = (tseq / NS) & 1u;
         prof.start();
@@ -355,7 +368,8 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
         prof.lap(0);
         const uint32_t ya = smem_u32(sY + slot * kSlotBytes) + trow * (uint32_t)(YW * 4);
         if (!(p.ablate & 2u) && active) {
-          if (fast) bq_tile(st, ya);
+          if (sym) bq_tile(ss, ya);
+          else if (fast) bq_tile(st, ya);
           else { // generic cascade: stage-major over the tile like the reference (filter_biquad.cpp:44-79); state in global
             for (int j = 0; j < nst; ++j) {
               BQ gs[1];
@@ -369,6 +383,9 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
         __syncwarp();
         if (lane == 0) mbar_arrive(isA ? &pc->ab_full[slot][q] : &pc->st_full[slot]);
         prof.lap(1);
+      }
+      if constexpr (std::is_same<BQ, BqStageW>::value) {
+        if (sym && active) static_cast<BqStage &>(st[0]) = static_cast<const BqStage &>(ss[0]);
       }
       if (fast && active) bq_store_stage(st[0], fl, p.bq, p.Cpad, obj, 0, ch);
     }
@@ -427,6 +444,7 @@ cudaError_t launch_chain_v5(const ChainParams &p_in, cudaStream_t stream, int va
   using namespace v5;
   ChainParams p = p_in;
   p.ablate = ((uint32_t)variant >> 4) & 3u;
+  if (getenv("MSDR_NOSYM")) p.ablate |= 4u; // study: never the four-product stage for symmetric numerators
   const size_t smem = smem_bytes(p.tc_K, p.tc_ring);
   // study knobs: variant bit 0 = all five products as IMAD.HI, bit 1 = feed-forward products as DFMA; default = IMAD.WIDE for the
   // four products off the recurrence
