@@ -9,6 +9,7 @@
 // K-block; the two epilogue warps of a TMEM lane quadrant already take the two 32-column halves of a tile, so each parks its own
 // half-slot; the biquad warps run the half-slots in time order.  Same roles, same warps, same arithmetic and the same plan as
 // msdr_chain_v5.cu; reference semantics as there (Minimal-SDR.ino:546-558,589-628, arm_fir_fast_q15.c:60-329, filter_biquad.cpp:33-82).
+#include <type_traits>
 #include "msdr_chain_v5_common.cuh"
 
 namespace msdr {
@@ -312,6 +313,17 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
       }
       const bool fast = __all_sync(0xffffffffu, nst == 1);
       if (fast && active) bq_load_stage(st[0], fl, p.bq, p.Cpad, obj, 0, ch);
+      // symmetric numerators (b0 == b2) in every lane: the four-product form of the stage (msdr_device.cuh: BqStageWS)
+      bool sym = false;
+      BqStageWS ss[1];
+      if constexpr (std::is_same<BQ, BqStageW>::value) {
+        sym = fast && __all_sync(0xffffffffu, !active || st[0].b0 == st[0].b2);
+        if (sym && active) {
+          static_cast<BqStage &>(ss[0]) = static_cast<const BqStage &>(st[0]);
+          ss[0].p1 = mulhi_wide(st[0].b0, st[0].x1);
+          ss[0].p2 = mulhi_wide(st[0].b0, st[0].x2);
+        }
+      }
       for (uint32_t u = 0; u < 2 * NT; ++u, ++useq) {
         const uint32_t slot = useq % NH, phs = (useq / NH) & 1u;
         prof.start();
@@ -319,7 +331,8 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
         prof.lap(0);
         const uint32_t ya = smem_u32(sY + slot * kHalfBytes) + trow * HP;
         if (!(p.ablate & 2u) && active) {
-          if (fast) bq_tile<BQ, HU / 8>(st, ya);
+          if (sym) bq_tile<BqStageWS, HU / 8>(ss, ya);
+          else if (fast) bq_tile<BQ, HU / 8>(st, ya);
           else { // generic cascade: stage-major over the unit like the reference (filter_biquad.cpp:44-79); state in global
             for (int j = 0; j < nst; ++j) {
               BQ gs[1];
@@ -333,6 +346,9 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
         __syncwarp();
         if (lane == 0) mbar_arrive(isA ? &pc->ab_full[slot][q] : &pc->st_full[slot]);
         prof.lap(1);
+      }
+      if constexpr (std::is_same<BQ, BqStageW>::value) {
+        if (sym && active) static_cast<BqStage &>(st[0]) = static_cast<const BqStage &>(ss[0]);
       }
       if (fast && active) bq_store_stage(st[0], fl, p.bq, p.Cpad, obj, 0, ch);
     }
