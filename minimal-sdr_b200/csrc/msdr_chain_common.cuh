@@ -167,6 +167,16 @@ __device__ __forceinline__ uint32_t bq_word(BqStageWS (&st)[NS], uint32_t w)
   for (int k = 0; k < NS; ++k) xo = bq_step(st[k], xo);
   return __byte_perm((uint32_t)xe, (uint32_t)xo, 0x7632);
 }
+template <int NS>
+__device__ __forceinline__ uint32_t bq_word(BqStageHS (&st)[NS], uint32_t w)
+{
+  int xe = (int)(w << 16), xo = (int)(w & 0xFFFF0000u);
+#pragma unroll
+  for (int k = 0; k < NS; ++k) xe = bq_step(st[k], xe);
+#pragma unroll
+  for (int k = 0; k < NS; ++k) xo = bq_step(st[k], xo);
+  return __byte_perm((uint32_t)xe, (uint32_t)xo, 0x7632);
+}
 // same on the FP64 pipe (D-form values)
 template <int NS>
 __device__ __forceinline__ uint32_t bq_word(BqStageD (&st)[NS], uint32_t w)

@@ -352,13 +352,15 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
       if (fast && active) bq_load_stage(st[0], fl, p.bq, p.Cpad, obj, 0, ch);
       // symmetric numerators (b0 == b2) in every lane: the four-product form of the stage (msdr_device.cuh: BqStageWS)
       bool sym = false;
-      BqStageWS ss[1];
-      if constexpr (std::is_same<BQ, BqStageW>::value) {
+      using SYM = typename BqSymOf<BQ>::type;
+      constexpr bool kHasSym = !std::is_same<SYM, void>::value;
+      typename std::conditional<kHasSym, SYM, BqStageWS>::type ss[1];
+      if constexpr (kHasSym) {
         sym = fast && !(p.ablate & 4u) && __all_sync(0xffffffffu, !active || st[0].b0 == st[0].b2);
         if (sym && active) {
           static_cast<BqStage &>(ss[0]) = static_cast<const BqStage &>(st[0]);
-          ss[0].p1 = mulhi_wide(st[0].b0, st[0].x1);
-          ss[0].p2 = mulhi_wide(st[0].b0, st[0].x2);
+          ss[0].p1 = __mulhi(st[0].b0, st[0].x1);
+          ss[0].p2 = __mulhi(st[0].b0, st[0].x2);
         }
       }
       for (uint32_t t = 0; t < NT; ++t, ++tseq) {
@@ -384,7 +386,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
         if (lane == 0) mbar_arrive(isA ? &pc->ab_full[slot][q] : &pc->st_full[slot]);
         prof.lap(1);
       }
-      if constexpr (std::is_same<BQ, BqStageW>::value) {
+      if constexpr (kHasSym) {
         if (sym && active) static_cast<BqStage &>(st[0]) = static_cast<const BqStage &>(ss[0]);
       }
       if (fast && active) bq_store_stage(st[0], fl, p.bq, p.Cpad, obj, 0, ch);
@@ -446,9 +448,9 @@ cudaError_t launch_chain_v5(const ChainParams &p_in, cudaStream_t stream, int va
   p.ablate = ((uint32_t)variant >> 4) & 3u;
   if (getenv("MSDR_NOSYM")) p.ablate |= 4u; // study: never the four-product stage for symmetric numerators
   const size_t smem = smem_bytes(p.tc_K, p.tc_ring);
-  // study knobs: variant bit 0 = all five products as IMAD.HI, bit 1 = feed-forward products as DFMA; default = IMAD.WIDE for the
-  // four products off the recurrence
-  auto kern = (variant & 12) == 12 ? chain_kernel<BqStageS> : (variant & 1) ? chain_kernel<BqStage> : (variant & 2) ? chain_kernel<BqStageH> : (variant & 4) ? chain_kernel<BqStageC> : (variant & 8) ? chain_kernel<BqStageE> : chain_kernel<BqStageW>;
+  // default: the products as IMAD.HI (with the looped epilogue 352 against 339 Gsamples/s at C5 for the IMAD.WIDE form, which was 1.5 %
+  // ahead before); study knobs: variant bit 0 = IMAD.WIDE for the four products off the recurrence, bit 1 = feed-forward products as DFMA
+  auto kern = (variant & 12) == 12 ? chain_kernel<BqStageS> : (variant & 1) ? chain_kernel<BqStageW> : (variant & 2) ? chain_kernel<BqStageH> : (variant & 4) ? chain_kernel<BqStageC> : (variant & 8) ? chain_kernel<BqStageE> : chain_kernel<BqStage>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const uint32_t grid = p.n_items < (uint32_t)sms ? p.n_items : (uint32_t)sms;

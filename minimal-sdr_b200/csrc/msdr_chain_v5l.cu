@@ -315,13 +315,15 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
       if (fast && active) bq_load_stage(st[0], fl, p.bq, p.Cpad, obj, 0, ch);
       // symmetric numerators (b0 == b2) in every lane: the four-product form of the stage (msdr_device.cuh: BqStageWS)
       bool sym = false;
-      BqStageWS ss[1];
-      if constexpr (std::is_same<BQ, BqStageW>::value) {
+      using SYM = typename BqSymOf<BQ>::type;
+      constexpr bool kHasSym = !std::is_same<SYM, void>::value;
+      typename std::conditional<kHasSym, SYM, BqStageWS>::type ss[1];
+      if constexpr (kHasSym) {
         sym = fast && __all_sync(0xffffffffu, !active || st[0].b0 == st[0].b2);
         if (sym && active) {
           static_cast<BqStage &>(ss[0]) = static_cast<const BqStage &>(st[0]);
-          ss[0].p1 = mulhi_wide(st[0].b0, st[0].x1);
-          ss[0].p2 = mulhi_wide(st[0].b0, st[0].x2);
+          ss[0].p1 = __mulhi(st[0].b0, st[0].x1);
+          ss[0].p2 = __mulhi(st[0].b0, st[0].x2);
         }
       }
       for (uint32_t u = 0; u < 2 * NT; ++u, ++useq) {
@@ -331,7 +333,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
         prof.lap(0);
         const uint32_t ya = smem_u32(sY + slot * kHalfBytes) + trow * HP;
         if (!(p.ablate & 2u) && active) {
-          if (sym) bq_tile<BqStageWS, HU / 8>(ss, ya);
+          if (sym) bq_tile<typename std::conditional<kHasSym, SYM, BqStageWS>::type, HU / 8>(ss, ya);
           else if (fast) bq_tile<BQ, HU / 8>(st, ya);
           else { // generic cascade: stage-major over the unit like the reference (filter_biquad.cpp:44-79); state in global
             for (int j = 0; j < nst; ++j) {
@@ -347,7 +349,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
         if (lane == 0) mbar_arrive(isA ? &pc->ab_full[slot][q] : &pc->st_full[slot]);
         prof.lap(1);
       }
-      if constexpr (std::is_same<BQ, BqStageW>::value) {
+      if constexpr (kHasSym) {
         if (sym && active) static_cast<BqStage &>(st[0]) = static_cast<const BqStage &>(ss[0]);
       }
       if (fast && active) bq_store_stage(st[0], fl, p.bq, p.Cpad, obj, 0, ch);

@@ -330,7 +330,7 @@ def test_update_range_device(msdr, orc, K):
                                             (2048, "tensor-core FIR + post warps"),
                                             (256, "tensor-core FIR, inline epilogue"), (128, "helper warps, forced"), (64, "CUDA-core FIR (v3)"),
                                             (65, "v3, FP64 biquad"), (4096, "row-block kernel (msdr_chain_v5.cu), forced"),
-                                            (4097, "row-block kernel, IMAD.HI stages"), (4098, "row-block kernel, DFMA feed-forward"),
+                                            (4097, "row-block kernel, IMAD.WIDE stages"), (4098, "row-block kernel, DFMA feed-forward"),
                                             (4100, "row-block kernel, chained DFMA feed-forward"), (4104, "row-block kernel, all five products one DFMA chain"),
                                             (4108, "row-block kernel, split 16 x 16-bit products")])
 def test_every_kernel_shape_is_bit_exact(msdr, orc, K, variant, name):
