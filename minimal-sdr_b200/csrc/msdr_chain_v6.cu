@@ -456,7 +456,11 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const ChainParams p)
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const uint32_t u0 = iq[2 * j] ^ xm, u1 = iq[2 * j + 1] ^ xm;
+#ifdef MSDR_V6_EPI_IMAD
+                o[j] = __byte_perm(u0 * 65537u + xc, u1 * 65537u + xc, 0x7632);
+#else
                 o[j] = __byte_perm(u0 + shl16_alu(u0) + xc, u1 + shl16_alu(u1) + xc, 0x7632);
+#endif
               }
             } else { // envelope kinds: eight square roots in flight
               int y[8];
