@@ -158,7 +158,12 @@ __global__ void frontend_kernel(const Params p)
             const uint32_t code = k ? __byte_perm(w[i], 0u, 0x4432) : __byte_perm(w[i], 0u, 0x4410);
             const int tmp = (int)(code * 16384u);
             const int acc = (int)((uint32_t)y1 - (uint32_t)x1 + (uint32_t)tmp);
-            y1 = (int)(((long long)acc * (long long)kCoefHpf) >> 30); // FRACMUL_SHL(acc, COEF, 1): bits [61:30] of the product
+            // FRACMUL_SHL(acc, COEF, 1): bits [61:30] of the product.  4 * COEF = 2^32 - 69 * 2^14, so
+            //   (acc * COEF) >> 30 = (acc * 4 COEF) >> 32 = acc + floor(-69 * 2^14 * acc / 2^32) = acc + mulhi(acc, -69 << 14)
+            // exactly: one IMAD.HI and an add (13 cycles of dependent latency) instead of IMAD.WIDE and a 64-bit funnel shift (20) on the
+            // per-sample recurrence.
+            static_assert(4ll * kCoefHpf == (1ll << 32) - (69ll << 14), "the identity above is derived from this coefficient");
+            y1 = acc + __mulhi(acc, -(69 << 14));
             x1 = tmp;
             int ss; // SSAT16(y1 >> 14) in the upper half (signed_saturate_rshift, input_adc.cpp:209)
             asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(ss) : "r"(y1 >> 14), "r"(0));
