@@ -18,18 +18,24 @@
 // its own 16 new words - the rows overlap in memory, each sample is converted once.  N = 32 (the first 32 columns of the same Toeplitz
 // operand the other kernels use, read in place through the descriptor strides).
 //
-// 16 warps, roles by warp id (warp id % 4 = SM sub-partition):
-//   7        load      cp.async (LDGSTS) of the tile's raw rows (16 rows x 512 B, gathered through the row map) into a 2-stage staging ring
-//   14, 15   convert   (row, unit) tasks: raw int16 -> fs/4 sign fold -> four byte planes; carries the window tail to the next span's buffer
+// A group block is two half blocks of 16 same-table channels (a tile each), each half with its own Toeplitz operand; the plan pairs a
+// half with an envelope demodulator (a square root per sample) with an SSB half, so that every CTA carries the same load.
+//
+// 16 warps (13 used), roles by warp id (warp id % 4 = SM sub-partition):
+//   7        load      cp.async (LDGSTS) of a tile's raw rows (16 rows x 512 B, gathered through the row map) into a 2-stage staging ring
+//   14, 15   convert   (row, unit) tasks: raw int16 -> fs/4 sign fold -> four byte planes in one of three operand buffers; the window tail
+//                      of the same half's previous tile is copied in front (16-byte copies), the carried history at sample 0
 //   6        MMA       one elected lane: 2 branches x 4 byte-plane products x K/32 MMAs (M128 N32 K32) per tile; two tiles live in TMEM
-//   0-3      epilogue  TMEM lane = (time block, channel): tcgen05.ld, recombine, >>15, SSAT16, demodulate -> 64 B of the span buffer
-//   10       FF1       lane = channel: span buffer -> e[n] of object 1 (the three input-side products, exact DFMA.RM) in a sub-tile slot
-//   4        chain A   recurrence of object 1 over the slot
-//   11       FF2       A's output -> e[n] of object 2
-//   5        chain B   recurrence of object 2
-//   8        store     slot -> `out`
+//   0-3      epilogue  TMEM lane = (time block, channel); per 8-column pass: tcgen05.ld, recombine, >>15, SSAT16, demodulate -> scratch;
+//                      then TMEM is handed back and the 64 bytes go into the span buffer (32 channels x 256 samples, two of them)
+//   10       FF1       lane = channel: span buffer -> e[n] of object 1 (the input-side products of the stage) into a slot of ring 1
+//   4        chain A   recurrence of object 1 over the slot, results in place over the consumed e[n] words
+//   11       FF2       A's results -> e[n] of object 2 into a slot of ring 2
+//   5        chain B   recurrence of object 2, in place
+//   9        store     ring-2 slot -> `out`
 // Chain A, chain B, FF1 and FF2 each have a sub-partition of their own; everything else is light (a CTA produces only what its own 32
-// channels consume).  DRAM traffic is the algorithmic 2 B in + 2 B out per sample.
+// channels consume).  DRAM traffic is the algorithmic 2 B in + 2 B out per sample.  Loops over column passes and sample groups are kept
+// rolled on purpose: the kernel is sensitive to its instruction-cache footprint.
 #include <cstdlib>
 #include "msdr_chain_v5_common.cuh"
 
