@@ -551,7 +551,7 @@ def main():
                       "latency_bound": {"cycles_per_sample_step": LATENCY_BOUND_CYCLES, "ceiling": lat_ceiling, "frac": per_gpu / lat_ceiling,
                                         "what": "machine bound: loop-carried latency of one stage (IMAD.HI 9 + SHF 4 + I2IP 4), every channel's chain running alone"},
                       "issue_bound_one_warp": {"cycles_per_sample_step": ISSUE_BOUND_CYCLES, "ceiling": iss_ceiling, "frac": per_gpu / iss_ceiling,
-                                               "what": "this build's own instruction sequence for a whole stage in one warp (tools/microbench/bqstep2.cu); not a machine bound"},
+                                               "what": "a whole stage in ONE warp, 43.5 cycles per sample (tools/microbench/bqstep2.cu): round 1's reference point, not a machine bound - the time-folded kernel splits a stage over a helper warp and a chain warp and exceeds it"},
                       "unit": "Msamples/s per GPU", "source": "profiles/r01_microbench_lat.txt; DESIGN.md section 6"}
         traffic, traffic_algo, traffic_src = ncu_traffic(w.name)
         line = {
