@@ -611,7 +611,8 @@ int build_tc_plan(msdr_chain *chain, uint32_t ch0, uint32_t nch, uint32_t sms, b
   pl.K = K;
   pl.ring_v5 = chain_v5_config(K, smem_max);
   pl.ring_v5l = chain_v5l_config(K, smem_max);
-  pl.slots_v6 = chain_v6_config(K, smem_max);
+  // (the time-folded kernel takes one group block per SM at most: no point in its row plan for wide ranges unless a study variant forces it)
+  pl.slots_v6 = (nch <= 8192u || (chain->variant & 65536)) ? chain_v6_config(K, smem_max) : 0u;
   pl.dual = want_dual && pl.rings[3] != 0;
   const uint32_t W = pl.W = sms * (pl.dual ? 2u : 1u);
 
